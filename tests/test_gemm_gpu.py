@@ -1,0 +1,90 @@
+"""tcgen05 GEMM (gecco_gemm) against a plain fp32 torch reference on the same bf16-rounded operands."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias=None, alpha=None, res=None):
+    out = a.float() @ w.float().t()
+    if bias is not None:
+        out = out + bias
+    if alpha is not None:
+        out = ((-(out**2) / (2 * alpha**2)).exp() - 0.7) / 0.28
+    if res is not None:
+        out = out + res
+    return out
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 192, 64), (256, 384, 384), (1000, 768, 768), (4096, 1152, 384), (300, 200, 136)])
+def test_gemm_plain(cuda, m, n, k):
+    from gecco_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda).bfloat16()
+    o32, o16 = ops.gemm(a, w, out_f32=True, out_bf16=True)
+    torch.cuda.synchronize()
+    ref = _ref(a, w)
+    err = (o32 - ref).abs().max().item()
+    assert err < 2e-3, err
+    assert (o16.float() - ref).abs().max().item() < 3e-2
+
+
+def test_gemm_epilogue_full(cuda):
+    from gecco_b200 import ops
+
+    B, N, Np, C = 3, 200, 256, 384
+    g = torch.Generator(device="cpu").manual_seed(7)
+    a = torch.randn(B * Np, 768, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(C, 768, generator=g) / math.sqrt(768)).to(cuda).bfloat16()
+    bias = torch.randn(C, generator=g).to(cuda)
+    res = torch.randn(B * Np, C, generator=g).to(cuda)
+    stats = torch.zeros(B, C // 12, 2, dtype=torch.float64, device=cuda)
+    x = res.clone()
+    ops.gemm(a, w, bias=bias, res=x, out_f32=x, stats=stats, rows_per_cloud=Np, valid_rows=N)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, bias=bias, res=res)
+    assert (x - ref).abs().max().item() < 2e-3
+    v = ref.view(B, Np, C // 12, 12)[:, :N].double()
+    s1 = v.sum(dim=(1, 3))
+    s2 = (v * v).sum(dim=(1, 3))
+    assert torch.allclose(stats[..., 0], s1, rtol=1e-4, atol=1e-2), (stats[..., 0] - s1).abs().max()
+    assert torch.allclose(stats[..., 1], s2, rtol=1e-4, atol=1e-2), (stats[..., 1] - s2).abs().max()
+
+
+def test_gemm_act_and_percloud_weights(cuda):
+    from gecco_b200 import ops
+
+    B, Np, K, C = 4, 128, 704, 384
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = torch.randn(B * Np, K, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(B * C, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    bias = torch.randn(B, C, generator=g).to(cuda)
+    o32, _ = ops.gemm(a, w, bias=bias, bias_stride=C, act_alpha=1.3, out_f32=True, rows_per_cloud=Np,
+                      w_rows_per_cloud=C, n_out=C)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ref = _ref(a[b * Np:(b + 1) * Np], w[b * C:(b + 1) * C], bias=bias[b], alpha=1.3)
+        assert (o32[b * Np:(b + 1) * Np] - ref).abs().max().item() < 5e-3
+
+
+def test_gemm_xyz_embed(cuda):
+    from gecco_b200 import ops
+
+    B, Np, K, C = 2, 128, 128, 192
+    g = torch.Generator(device="cpu").manual_seed(13)
+    a = torch.randn(B * Np, K, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(C, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    bias = torch.randn(C, generator=g).to(cuda)
+    geom = torch.randn(B * Np, 3, generator=g).to(cuda)
+    wx = torch.randn(C, 3, generator=g).to(cuda)
+    sigma = torch.tensor([0.5, 7.0], device=cuda)
+    o32, _ = ops.gemm(a, w, bias=bias, out_f32=True, rows_per_cloud=Np, geom=geom, sigma=sigma, sigma_stride=1, wx=wx)
+    torch.cuda.synchronize()
+    c_in = 1 / (1 + sigma**2).sqrt()
+    gg = geom.view(B, Np, 3) * c_in.view(B, 1, 1)
+    ref = _ref(a, w, bias=bias) + (gg.view(-1, 3) @ wx.t())
+    assert (o32 - ref).abs().max().item() < 2e-3
