@@ -31,8 +31,90 @@ class GemmArgs(C.Structure):
         ("out_bf16", C.c_void_p), ("ldo16", C.c_int64),
         ("stats", C.c_void_p),
         ("geom", C.c_void_p),
-        ("sigma", C.c_void_p), ("sigma_stride", C.c_int32),
+        ("sigma", C.c_void_p), ("sigma_stride", C.c_int32), ("sigma_data", C.c_float),
         ("wx", C.c_void_p),
+    ]
+
+
+class AdaGNArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("stats", C.c_void_p), ("stat_gs", C.c_int32),
+        ("t", C.c_void_p), ("t_stride", C.c_int32), ("ctx_dim", C.c_int32),
+        ("scale_w", C.c_void_p), ("scale_b", C.c_void_p), ("bias_w", C.c_void_p), ("bias_b", C.c_void_p),
+        ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32), ("valid_rows", C.c_int32), ("c", C.c_int32),
+        ("groups", C.c_int32),
+        ("eps", C.c_float),
+        ("out_bf16", C.c_void_p), ("ldo16", C.c_int64),
+        ("out_f32", C.c_void_p), ("ldo32", C.c_int64),
+    ]
+
+
+class LiftArgs(C.Structure):
+    _fields_ = [
+        ("xin", C.c_void_p),
+        ("sigma", C.c_void_p), ("sigma_stride", C.c_int32), ("sigma_data", C.c_float),
+        ("w", C.c_void_p), ("b", C.c_void_p),
+        ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32), ("valid_rows", C.c_int32), ("c", C.c_int32),
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("stats", C.c_void_p), ("stat_gs", C.c_int32),
+    ]
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32), ("valid_rows", C.c_int32), ("c", C.c_int32),
+        ("norm", C.c_int32), ("groups", C.c_int32), ("stats", C.c_void_p), ("stat_gs", C.c_int32), ("eps", C.c_float),
+        ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+        ("xin", C.c_void_p),
+        ("sigma", C.c_void_p), ("sigma_stride", C.c_int32), ("sigma_data", C.c_float),
+        ("mode", C.c_int32),
+        ("out_f32", C.c_void_p),
+        ("x_hat", C.c_void_p), ("x_next", C.c_void_p), ("d_cur", C.c_void_p), ("xin_next", C.c_void_p),
+        ("noise_next", C.c_void_p),
+        ("t_hat", C.c_double), ("t_next", C.c_double), ("churn_next", C.c_double),
+    ]
+
+
+MAX_LEVELS = 4
+
+
+class LookupArgs(C.Structure):
+    _fields_ = [
+        ("xin", C.c_void_p),
+        ("sigma", C.c_void_p), ("sigma_stride", C.c_int32), ("sigma_data", C.c_float),
+        ("reparam", C.c_int32),
+        ("mean", C.c_float * 3), ("sigma_r", C.c_float * 3), ("logit_scale", C.c_float),
+        ("K", C.c_void_p),
+        ("n_levels", C.c_int32),
+        ("level_ptr", C.c_void_p * MAX_LEVELS),
+        ("level_h", C.c_int32 * MAX_LEVELS), ("level_w", C.c_int32 * MAX_LEVELS), ("level_c", C.c_int32 * MAX_LEVELS),
+        ("clouds", C.c_int32), ("points", C.c_int32), ("rows_per_cloud", C.c_int32),
+        ("out_bf16", C.c_void_p), ("ldo16", C.c_int64),
+        ("out_f32", C.c_void_p), ("ldo32", C.c_int64),
+        ("stats", C.c_void_p), ("stat_groups", C.c_int32),
+    ]
+
+
+class PoolArgs(C.Structure):
+    _fields_ = [
+        ("kv", C.c_void_p), ("ld", C.c_int64), ("k_off", C.c_int32), ("v_off", C.c_int32),
+        ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32), ("valid_rows", C.c_int32),
+        ("heads", C.c_int32), ("head_dim", C.c_int32), ("inducers", C.c_int32),
+        ("q_inducers", C.c_void_p),
+        ("splits", C.c_int32), ("partial", C.c_void_p),
+        ("out_bf16", C.c_void_p), ("ldo", C.c_int64),
+    ]
+
+
+class UnpoolArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("kv", C.c_void_p), ("ldkv", C.c_int64), ("v_off", C.c_int32),
+        ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32),
+        ("heads", C.c_int32), ("head_dim", C.c_int32), ("inducers", C.c_int32),
+        ("out_bf16", C.c_void_p), ("ldo", C.c_int64),
     ]
 
 

@@ -1,0 +1,466 @@
+// HBM-bound row-wise kernels around the tensor-core GEMMs:
+//   group statistics, AdaGN apply (fp32 -> bf16 operand), unconditional lift, output head + EDM step,
+//   reparametrisations.  All are coalesced over the channel dimension (one float4 per thread).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace gecco {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Group statistics: stats[cloud][c / gs][{sum, sumsq}] over the valid rows of each cloud (double).
+// grid (row chunks, clouds), block C/4 threads (looping if C/4 > blockDim).
+constexpr int STAT_ROWS = 64;
+
+__global__ void group_stats_kernel(const float* __restrict__ x, long long ldx, int rows_per_cloud, int valid_rows,
+                                   int C, int gs, double* __restrict__ stats) {
+  extern __shared__ float sgrp[];  // [C/gs][2]
+  const int ngroups = C / gs;
+  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.f;
+  __syncthreads();
+  const int cloud = blockIdx.y;
+  const int r0 = blockIdx.x * STAT_ROWS;
+  const int r1 = min(r0 + STAT_ROWS, valid_rows);
+  const float* base = x + ((long long)cloud * rows_per_cloud) * ldx;
+  for (int cq = threadIdx.x; cq < C / 4; cq += blockDim.x) {
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (long long)r * ldx + cq * 4);
+      s1[0] += v.x; s2[0] += v.x * v.x;
+      s1[1] += v.y; s2[1] += v.y * v.y;
+      s1[2] += v.z; s2[2] += v.z * v.z;
+      s1[3] += v.w; s2[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (cq * 4 + j) / gs;
+      atomicAdd(&sgrp[g * 2], s1[j]);
+      atomicAdd(&sgrp[g * 2 + 1], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x)
+    atomicAdd(stats + (long long)cloud * ngroups * 2 + i, static_cast<double>(sgrp[i]));
+}
+
+// mean / rstd of normalisation group `g` (of `gs` channels) from statistics kept at `sgs`-channel
+// granularity (gs % sgs == 0): sums of gs/sgs consecutive fine groups.
+__device__ __forceinline__ void group_mean_rstd(const double* __restrict__ cstats, int g, int gs, int sgs, double count,
+                                                float eps, float& mean, float& rstd) {
+  const int per = gs / sgs;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < per; ++i) {
+    s1 += cstats[(g * per + i) * 2];
+    s2 += cstats[(g * per + i) * 2 + 1];
+  }
+  const double m = s1 / count;
+  double var = s2 / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = static_cast<float>(m);
+  rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdaGN apply (models/normalization.py:36-44): y = scale(t) * (x - mean_g) * rstd_g + bias(t)
+// with scale(t) = t . scale_w[c, :] + scale_b[c] (same for bias).  Padding rows are written as 0.
+constexpr int ADAGN_ROWS = 32;
+
+__global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, const double* __restrict__ stats,
+                                   int stat_gs, const float* __restrict__ t, int t_stride, int ctx_dim,
+                                   const float* __restrict__ scale_w, const float* __restrict__ scale_b,
+                                   const float* __restrict__ bias_w, const float* __restrict__ bias_b,
+                                   int rows_per_cloud, int valid_rows, int C, int groups, float eps,
+                                   __nv_bfloat16* __restrict__ out16, long long ldo16, float* __restrict__ out32,
+                                   long long ldo32) {
+  const int cloud = blockIdx.y;
+  const int r0 = blockIdx.x * ADAGN_ROWS;
+  const int r1 = min(r0 + ADAGN_ROWS, rows_per_cloud);
+  const int gs = C / groups;
+  const double count = static_cast<double>(valid_rows) * gs;
+  const double* cstats = stats + (long long)cloud * (C / stat_gs) * 2;
+  const long long row_base = (long long)cloud * rows_per_cloud;
+  for (int cq = threadIdx.x; cq < C / 4; cq += blockDim.x) {
+    float a[4], s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cq * 4 + j;
+      float mean, rstd;
+      group_mean_rstd(cstats, c / gs, gs, stat_gs, count, eps, mean, rstd);
+      float sc = __ldg(scale_b + c), bi = __ldg(bias_b + c);
+      for (int i = 0; i < ctx_dim; ++i) {
+        const float ti = __ldg(t + (long long)cloud * t_stride + i);
+        sc += ti * __ldg(scale_w + (long long)c * ctx_dim + i);
+        bi += ti * __ldg(bias_w + (long long)c * ctx_dim + i);
+      }
+      a[j] = sc * rstd;
+      s[j] = bi - sc * rstd * mean;
+    }
+    for (int r = r0; r < r1; ++r) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < valid_rows) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (row_base + r) * ldx + cq * 4);
+        v.x = a[0] * xv.x + s[0];
+        v.y = a[1] * xv.y + s[1];
+        v.z = a[2] * xv.z + s[2];
+        v.w = a[3] * xv.w + s[3];
+      }
+      if (out16 != nullptr) {
+        uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(out16 + (row_base + r) * ldo16 + cq * 4) = pk;
+      }
+      if (out32 != nullptr) *reinterpret_cast<float4*>(out32 + (row_base + r) * ldo32 + cq * 4) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Unconditional lift (models/linear_lift.py:21,44): x = W (c_in * xin) + b, plus AdaGN statistics of x
+// at `gs`-channel granularity.  Padding rows are written as 0.
+constexpr int LIFT_ROWS = 32;
+
+__global__ void lift_kernel(const float* __restrict__ xin, const float* __restrict__ sigma, int sigma_stride,
+                            float sigma_data, const float* __restrict__ w, const float* __restrict__ b,
+                            int rows_per_cloud, int valid_rows, int C, int gs, float* __restrict__ x, long long ldx,
+                            double* __restrict__ stats) {
+  extern __shared__ float sgrp[];
+  const int ngroups = C / gs;
+  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.f;
+  __syncthreads();
+  const int cloud = blockIdx.y;
+  const int r0 = blockIdx.x * LIFT_ROWS;
+  const int r1 = min(r0 + LIFT_ROWS, rows_per_cloud);
+  float c_in = 1.f;
+  if (sigma != nullptr) {
+    const float sg = __ldg(sigma + (long long)cloud * sigma_stride);
+    c_in = 1.0f / sqrtf(sigma_data * sigma_data + sg * sg);
+  }
+  const long long row_base = (long long)cloud * rows_per_cloud;
+  for (int cq = threadIdx.x; cq < C / 4; cq += blockDim.x) {
+    float wv[4][3], bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cq * 4 + j;
+      wv[j][0] = __ldg(w + c * 3 + 0);
+      wv[j][1] = __ldg(w + c * 3 + 1);
+      wv[j][2] = __ldg(w + c * 3 + 2);
+      bv[j] = __ldg(b + c);
+    }
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int r = r0; r < r1; ++r) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < valid_rows) {
+        const float* g = xin + ((long long)cloud * valid_rows + r) * 3;
+        const float g0 = c_in * __ldg(g), g1 = c_in * __ldg(g + 1), g2 = c_in * __ldg(g + 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = bv[j] + g0 * wv[j][0] + g1 * wv[j][1] + g2 * wv[j][2];
+          s1[j] += o[j];
+          s2[j] += o[j] * o[j];
+        }
+      }
+      *reinterpret_cast<float4*>(x + (row_base + r) * ldx + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (stats != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (cq * 4 + j) / gs;
+        atomicAdd(&sgrp[g * 2], s1[j]);
+        atomicAdd(&sgrp[g * 2 + 1], s2[j]);
+      }
+    }
+  }
+  if (stats != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x)
+      atomicAdd(stats + (long long)cloud * ngroups * 2 + i, static_cast<double>(sgrp[i]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output head + EDM preconditioning + sampler update, one warp per point.
+//   F = W_out . norm(x_row) + b_out           (models/ray.py:56-59,120 / models/linear_lift.py:26-29,46)
+//   D = c_skip * xin + c_out * F              (diffusion.py:46-57)
+//   mode 2: Euler step, mode 3: Heun correction + churn of the next step (diffusion.py:317-347)
+constexpr int HEAD_WARPS = 8;
+constexpr int HEAD_MAX_PER_LANE = 32;  // C <= 1024
+
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+head_kernel(const gecco_head_args a) {
+  extern __shared__ float smem_head[];  // [groups][2] mean, rstd (GroupNorm mode)
+  const int cloud = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.c;
+  const int gs = (a.norm == 2) ? C / a.groups : 1;
+  if (a.norm == 2) {
+    const double count = static_cast<double>(a.valid_rows) * gs;
+    const double* cstats = a.stats + (long long)cloud * (C / a.stat_gs) * 2;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+      float mean, rstd;
+      group_mean_rstd(cstats, g, gs, a.stat_gs, count, a.eps, mean, rstd);
+      smem_head[g * 2] = mean;
+      smem_head[g * 2 + 1] = rstd;
+    }
+    __syncthreads();
+  }
+  const float sg = a.sigma != nullptr ? __ldg(a.sigma + (long long)cloud * a.sigma_stride) : 0.f;
+  const float sd = a.sigma_data;
+  const float c_skip = sd * sd / (sg * sg + sd * sd);
+  const float c_out = sg * sd / sqrtf(sg * sg + sd * sd);
+
+  const int nq = C / 128;  // float4 per lane
+  for (int r = blockIdx.x * HEAD_WARPS + warp; r < a.valid_rows; r += gridDim.x * HEAD_WARPS) {
+    const float* xr = a.x + ((long long)cloud * a.rows_per_cloud + r) * a.ldx;
+    float v[HEAD_MAX_PER_LANE];
+    for (int i = 0; i < nq; ++i) {
+      const float4 t4 = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+      v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+    }
+    if (a.norm == 1) {  // LayerNorm over channels, no affine
+      float s = 0.f;
+      for (int i = 0; i < 4 * nq; ++i) s += v[i];
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+      for (int i = 0; i < 4 * nq; ++i) { const float d = v[i] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) / C + a.eps);
+      for (int i = 0; i < 4 * nq; ++i) v[i] = (v[i] - mean) * rstd;
+    } else if (a.norm == 2) {
+      for (int i = 0; i < nq; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = i * 128 + lane * 4 + j;
+          const int g = c / gs;
+          v[4 * i + j] = (v[4 * i + j] - smem_head[g * 2]) * smem_head[g * 2 + 1];
+        }
+    }
+    float f[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      float acc = 0.f;
+      for (int i = 0; i < nq; ++i) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w_out + (long long)o * C + i * 128 + lane * 4));
+        acc += v[4 * i] * w4.x + v[4 * i + 1] * w4.y + v[4 * i + 2] * w4.z + v[4 * i + 3] * w4.w;
+      }
+      f[o] = warp_sum(acc) + __ldg(a.b_out + o);
+    }
+    if (lane < 3) {
+      const float F = lane == 0 ? f[0] : (lane == 1 ? f[1] : f[2]);
+      const long long idx = ((long long)cloud * a.valid_rows + r) * 3 + lane;
+      if (a.mode == 0) {
+        a.out_f32[idx] = F;
+      } else {
+        const float xi = a.xin[idx];
+        const float D = c_skip * xi + c_out * F;
+        if (a.mode == 1) {
+          a.out_f32[idx] = D;
+        } else if (a.mode == 2) {  // Euler
+          const double xh = a.x_hat[idx];
+          const double d_cur = (xh - static_cast<double>(D)) / a.t_hat;
+          const double xn = xh + (a.t_next - a.t_hat) * d_cur;
+          a.d_cur[idx] = d_cur;
+          a.x_next[idx] = xn;
+          a.xin_next[idx] = static_cast<float>(xn);
+        } else {  // Heun correction, then churn for the next step
+          const double xh = a.x_hat[idx];
+          const double xn = a.x_next[idx];
+          const double d_prime = (xn - static_cast<double>(D)) / a.t_next;
+          double xnew = xh + (a.t_next - a.t_hat) * (0.5 * a.d_cur[idx] + 0.5 * d_prime);
+          if (a.noise_next != nullptr) xnew = xnew + a.churn_next * static_cast<double>(a.noise_next[idx]);
+          a.x_hat[idx] = xnew;
+          a.xin_next[idx] = static_cast<float>(xnew);
+        }
+      }
+    }
+  }
+}
+
+// x_hat = scale0 * latents (+ churn * noise); also the fp32 network input.  (diffusion.py:308,323-325)
+__global__ void sampler_init_kernel(const float* __restrict__ latents, const float* __restrict__ noise, double t0,
+                                    double churn, long long n, double* __restrict__ x_hat, float* __restrict__ xin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = static_cast<double>(latents[i]) * t0;
+  if (noise != nullptr) x = x + churn * static_cast<double>(noise[i]);
+  x_hat[i] = x;
+  xin[i] = static_cast<float>(x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reparametrisations (reparam.py).  T = float or double.
+template <typename T>
+struct RP {
+  T mean[3], sigma[3];
+  T logit_scale;
+};
+
+template <typename T>
+__device__ __forceinline__ void project_pt(const T* p, const T* K, T& u, T& v) {
+  // kornia project_points: scale = |z| > 1e-8 ? 1/(z + 1e-8) : 1
+  const T z = p[2];
+  const T sc = (fabs(z) > T(1e-8)) ? T(1) / (z + T(1e-8)) : T(1);
+  u = p[0] * sc * K[0] + K[2];
+  v = p[1] * sc * K[4] + K[5];
+}
+
+template <typename T>
+__global__ void reparam_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ Kmat,
+                               int kind, int to_data, RP<T> rp, int points_per_cloud, long long n_points) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  T p[3] = {in[i * 3], in[i * 3 + 1], in[i * 3 + 2]};
+  T o[3];
+  if (kind == 1) {  // GaussianReparam, reparam.py:58-64
+    for (int j = 0; j < 3; ++j) o[j] = to_data ? p[j] * rp.sigma[j] + rp.mean[j] : (p[j] - rp.mean[j]) / rp.sigma[j];
+  } else if (kind == 2) {  // UVLReparam, reparam.py:122-201
+    T K[9];
+    const float* Kc = Kmat + (i / points_per_cloud) * 9;
+    for (int j = 0; j < 9; ++j) K[j] = static_cast<T>(Kc[j]);
+    if (to_data) {
+      T uvl[3];
+      for (int j = 0; j < 3; ++j) uvl[j] = p[j] * rp.sigma[j] + rp.mean[j];
+      const T h = (tanh(uvl[0]) * rp.logit_scale + T(1)) / T(2);
+      const T w = (tanh(uvl[1]) * rp.logit_scale + T(1)) / T(2);
+      const T d = exp(uvl[2]);
+      const T x = (h - K[2]) / K[0];
+      const T y = (w - K[5]) / K[4];
+      T nrm = sqrt(x * x + y * y + T(1));
+      nrm = nrm > T(1e-12) ? nrm : T(1e-12);
+      o[0] = x / nrm * d;
+      o[1] = y / nrm * d;
+      o[2] = T(1) / nrm * d;
+    } else {
+      T u, v;
+      project_pt(p, K, u, v);
+      const T d = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+      const T r0 = atanh((T(2) * u - T(1)) / rp.logit_scale);
+      const T r1 = atanh((T(2) * v - T(1)) / rp.logit_scale);
+      const T r2 = log(d);
+      o[0] = (r0 - rp.mean[0]) / rp.sigma[0];
+      o[1] = (r1 - rp.mean[1]) / rp.sigma[1];
+      o[2] = (r2 - rp.mean[2]) / rp.sigma[2];
+    }
+  } else {
+    for (int j = 0; j < 3; ++j) o[j] = p[j];
+  }
+  out[i * 3] = o[0];
+  out[i * 3 + 1] = o[1];
+  out[i * 3 + 2] = o[2];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host launchers (used by engine.cu too)
+int launch_group_stats(const float* x, long long ldx, int clouds, int rows_per_cloud, int valid_rows, int C, int gs,
+                       double* stats, cudaStream_t s) {
+  GECCO_REQUIRE(C % 4 == 0 && gs > 0 && C % gs == 0, "group_stats: bad channel layout C=%d gs=%d", C, gs);
+  GECCO_REQUIRE(ldx % 4 == 0, "group_stats: ldx must be a multiple of 4");
+  dim3 grid(ceil_div(valid_rows, STAT_ROWS), clouds);
+  const int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
+  group_stats_kernel<<<grid, threads, (C / gs) * 2 * sizeof(float), s>>>(x, ldx, rows_per_cloud, valid_rows, C, gs, stats);
+  GECCO_CHECK_LAUNCH("group_stats_kernel");
+  return GECCO_OK;
+}
+
+int launch_adagn(const gecco_adagn_args& a, cudaStream_t s) {
+  GECCO_REQUIRE(a.c % 4 == 0 && a.groups > 0 && a.c % a.groups == 0, "adagn: bad channel layout");
+  GECCO_REQUIRE(a.stat_gs > 0 && (a.c / a.groups) % a.stat_gs == 0, "adagn: group size %d is not a multiple of the statistics granularity %d",
+                a.c / a.groups, a.stat_gs);
+  GECCO_REQUIRE(a.out_bf16 || a.out_f32, "adagn: no output");
+  GECCO_REQUIRE(a.ldx % 4 == 0 && (!a.out_bf16 || a.ldo16 % 4 == 0) && (!a.out_f32 || a.ldo32 % 4 == 0), "adagn: bad leading dimension");
+  dim3 grid(ceil_div(a.rows_per_cloud, ADAGN_ROWS), a.clouds);
+  const int threads = a.c / 4 < 256 ? ((a.c / 4 + 31) / 32) * 32 : 256;
+  adagn_apply_kernel<<<grid, threads, 0, s>>>(a.x, a.ldx, a.stats, a.stat_gs, a.t, a.t_stride, a.ctx_dim, a.scale_w,
+                                             a.scale_b, a.bias_w, a.bias_b, a.rows_per_cloud, a.valid_rows, a.c,
+                                             a.groups, a.eps, static_cast<__nv_bfloat16*>(a.out_bf16), a.ldo16,
+                                             a.out_f32, a.ldo32);
+  GECCO_CHECK_LAUNCH("adagn_apply_kernel");
+  return GECCO_OK;
+}
+
+int launch_lift(const gecco_lift_args& a, cudaStream_t s) {
+  GECCO_REQUIRE(a.c % 4 == 0 && a.ldx % 4 == 0, "lift: bad channel layout");
+  GECCO_REQUIRE(!a.stats || (a.stat_gs > 0 && a.c % a.stat_gs == 0), "lift: bad statistics granularity");
+  dim3 grid(ceil_div(a.rows_per_cloud, LIFT_ROWS), a.clouds);
+  const int threads = a.c / 4 < 256 ? ((a.c / 4 + 31) / 32) * 32 : 256;
+  const int gs = a.stats ? a.stat_gs : a.c;
+  lift_kernel<<<grid, threads, (a.c / gs) * 2 * sizeof(float), s>>>(a.xin, a.sigma, a.sigma_stride, a.sigma_data, a.w, a.b,
+                                                                   a.rows_per_cloud, a.valid_rows, a.c, gs, a.x, a.ldx,
+                                                                   a.stats);
+  GECCO_CHECK_LAUNCH("lift_kernel");
+  return GECCO_OK;
+}
+
+int launch_head(const gecco_head_args& a, cudaStream_t s) {
+  GECCO_REQUIRE(a.c % 128 == 0 && a.c <= 128 * (HEAD_MAX_PER_LANE / 4), "head: C must be a multiple of 128 and <= 1024");
+  GECCO_REQUIRE(a.ldx % 4 == 0, "head: ldx must be a multiple of 4");
+  GECCO_REQUIRE(a.norm != 2 || (a.stats && a.groups > 0 && a.c % a.groups == 0 && (a.c / a.groups) % a.stat_gs == 0),
+                "head: GroupNorm needs statistics with a granularity dividing the group size");
+  GECCO_REQUIRE(a.mode >= 0 && a.mode <= 3, "head: bad mode");
+  GECCO_REQUIRE(a.mode == 0 || (a.xin && a.sigma), "head: preconditioning needs xin and sigma");
+  GECCO_REQUIRE(a.mode > 1 || a.out_f32, "head: no output");
+  GECCO_REQUIRE(a.mode < 2 || (a.x_hat && a.x_next && a.d_cur && a.xin_next), "head: sampler state missing");
+  int gx = ceil_div(a.valid_rows, HEAD_WARPS);
+  if (gx > 1024) gx = 1024;
+  dim3 grid(gx, a.clouds);
+  const size_t sm = a.norm == 2 ? a.groups * 2 * sizeof(float) : 0;
+  head_kernel<<<grid, HEAD_WARPS * 32, sm, s>>>(a);
+  GECCO_CHECK_LAUNCH("head_kernel");
+  return GECCO_OK;
+}
+
+int launch_sampler_init(const float* latents, const float* noise, double t0, double churn, long long n, double* x_hat,
+                        float* xin, cudaStream_t s) {
+  sampler_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(latents, noise, t0, churn, n, x_hat, xin);
+  GECCO_CHECK_LAUNCH("sampler_init_kernel");
+  return GECCO_OK;
+}
+
+}  // namespace gecco
+
+extern "C" int gecco_group_stats(const float* x, int64_t ldx, int32_t clouds, int32_t rows_per_cloud, int32_t valid_rows,
+                                 int32_t c, int32_t group_size, double* stats, void* stream) {
+  return gecco::launch_group_stats(x, ldx, clouds, rows_per_cloud, valid_rows, c, group_size, stats,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_adagn(const gecco_adagn_args* a, void* stream) {
+  if (!a) { gecco::set_error("gecco_adagn: null args"); return GECCO_ERR_INVALID; }
+  return gecco::launch_adagn(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_lift(const gecco_lift_args* a, void* stream) {
+  if (!a) { gecco::set_error("gecco_lift: null args"); return GECCO_ERR_INVALID; }
+  return gecco::launch_lift(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_head(const gecco_head_args* a, void* stream) {
+  if (!a) { gecco::set_error("gecco_head: null args"); return GECCO_ERR_INVALID; }
+  return gecco::launch_head(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_reparam(const void* in, void* out, int32_t is_double, int32_t kind, int32_t to_data,
+                             const float* mean, const float* sigma, float logit_scale, const float* K,
+                             int32_t clouds, int32_t points_per_cloud, void* stream) {
+  using namespace gecco;
+  GECCO_REQUIRE(kind >= 0 && kind <= 2, "reparam: unknown kind %d", kind);
+  GECCO_REQUIRE(kind != 2 || K != nullptr, "reparam: UVL needs the camera matrices");
+  const long long n = (long long)clouds * points_per_cloud;
+  if (n == 0) return GECCO_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (is_double) {
+    RP<double> rp;
+    for (int j = 0; j < 3; ++j) { rp.mean[j] = mean ? mean[j] : 0.0; rp.sigma[j] = sigma ? sigma[j] : 1.0; }
+    rp.logit_scale = logit_scale;
+    reparam_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(in), static_cast<double*>(out), K, kind,
+                                                  to_data, rp, points_per_cloud, n);
+  } else {
+    RP<float> rp;
+    for (int j = 0; j < 3; ++j) { rp.mean[j] = mean ? mean[j] : 0.f; rp.sigma[j] = sigma ? sigma[j] : 1.f; }
+    rp.logit_scale = logit_scale;
+    reparam_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float*>(out), K, kind,
+                                                 to_data, rp, points_per_cloud, n);
+  }
+  GECCO_CHECK_LAUNCH("reparam_kernel");
+  return GECCO_OK;
+}

@@ -45,6 +45,7 @@ struct KParams {
   const float* geom;
   const float* sigma;
   int sigma_stride;
+  float sigma_data;
   const float* wx;
   int num_m_blocks, num_n_blocks;
 };
@@ -147,12 +148,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const bool row_valid = row_ok && (row - cloud * p.rows_per_cloud) < p.valid_rows;
 
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (p.geom != nullptr && row_ok) {
+      if (p.geom != nullptr && row_valid) {
+        // geom is compact [clouds, valid_rows, 3]; output rows are padded to rows_per_cloud
         const float s = __ldg(p.sigma + (long long)cloud * p.sigma_stride);
-        const float c_in = 1.0f / sqrtf(1.0f + s * s);
-        g0 = c_in * __ldg(p.geom + (long long)row * 3 + 0);
-        g1 = c_in * __ldg(p.geom + (long long)row * 3 + 1);
-        g2 = c_in * __ldg(p.geom + (long long)row * 3 + 2);
+        const float c_in = 1.0f / sqrtf(p.sigma_data * p.sigma_data + s * s);
+        const float* gp = p.geom + ((long long)cloud * p.valid_rows + (row - cloud * p.rows_per_cloud)) * 3;
+        g0 = c_in * __ldg(gp + 0);
+        g1 = c_in * __ldg(gp + 1);
+        g2 = c_in * __ldg(gp + 2);
       }
 
       mbar_wait(&acc_full[slot], acc_phase);
@@ -334,7 +337,7 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   p.out_f32 = a.out_f32; p.ldo32 = a.ldo32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16); p.ldo16 = a.ldo16;
   p.stats = a.stats;
-  p.geom = a.geom; p.sigma = a.sigma; p.sigma_stride = a.sigma_stride; p.wx = a.wx;
+  p.geom = a.geom; p.sigma = a.sigma; p.sigma_stride = a.sigma_stride; p.sigma_data = a.sigma_data; p.wx = a.wx;
   p.num_m_blocks = ceil_div(a.m, BM);
   p.num_n_blocks = ceil_div(a.n_out, BN);
 

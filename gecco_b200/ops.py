@@ -50,6 +50,7 @@ def gemm(
     sigma: Tensor | None = None,
     sigma_stride: int = 0,
     wx: Tensor | None = None,
+    sigma_data: float = 1.0,
 ):
     """out = epilogue(a @ w.T) on the tcgen05 tensor cores; see gecco_gemm in include/gecco_b200.h."""
     lib = _lib_for(a)
@@ -96,5 +97,222 @@ def gemm(
         assert geom.dtype == torch.float32 and geom.is_contiguous()
         assert sigma is not None and wx is not None and sigma.dtype == torch.float32 and wx.dtype == torch.float32
         args.geom, args.sigma, args.sigma_stride, args.wx = geom.data_ptr(), sigma.data_ptr(), sigma_stride, wx.data_ptr()
+        args.sigma_data = sigma_data
     _abi.check(lib.gecco_gemm(C.byref(args), _stream(a)))
     return out_f32, out_bf16
+
+
+STAT_GS = 12  # channel granularity of the AdaGN statistics kept by the GEMM epilogue (C / 32 for C = 384)
+
+
+def group_stats(x: Tensor, rows_per_cloud: int, valid_rows: int, group_size: int, stats: Tensor | None = None) -> Tensor:
+    """stats[cloud, group, {sum, sumsq}] (float64) over the valid rows of each cloud; x is [clouds*rows_per_cloud, C]."""
+    lib = _lib_for(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    clouds = x.shape[0] // rows_per_cloud
+    c = x.shape[1]
+    if stats is None:
+        stats = torch.zeros((clouds, c // group_size, 2), device=x.device, dtype=torch.float64)
+    _abi.check(lib.gecco_group_stats(_ptr(x), C.c_int64(x.stride(0)), clouds, rows_per_cloud, valid_rows, c, group_size,
+                                     _ptr(stats), _stream(x)))
+    return stats
+
+
+def adagn(x: Tensor, stats: Tensor, stat_gs: int, t: Tensor, scale_w: Tensor, scale_b: Tensor, bias_w: Tensor,
+          bias_b: Tensor, *, rows_per_cloud: int, valid_rows: int, groups: int = 32, eps: float = 1e-5,
+          out_bf16: Tensor | bool | None = None, out_f32: Tensor | bool | None = None, t_stride: int | None = None):
+    lib = _lib_for(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, c = x.shape
+    clouds = rows // rows_per_cloud
+    ctx_dim = scale_w.shape[1] if scale_w.dim() == 2 else 1
+    if out_bf16 is True:
+        out_bf16 = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+    if out_f32 is True:
+        out_f32 = torch.empty((rows, c), device=x.device, dtype=torch.float32)
+    if out_bf16 is False:
+        out_bf16 = None
+    if out_f32 is False:
+        out_f32 = None
+    a = _abi.AdaGNArgs()
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    a.stats, a.stat_gs = stats.data_ptr(), stat_gs
+    a.t, a.t_stride, a.ctx_dim = t.data_ptr(), (ctx_dim if t_stride is None else t_stride), ctx_dim
+    a.scale_w, a.scale_b, a.bias_w, a.bias_b = scale_w.data_ptr(), scale_b.data_ptr(), bias_w.data_ptr(), bias_b.data_ptr()
+    a.clouds, a.rows_per_cloud, a.valid_rows, a.c, a.groups = clouds, rows_per_cloud, valid_rows, c, groups
+    a.eps = eps
+    if out_bf16 is not None:
+        a.out_bf16, a.ldo16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if out_f32 is not None:
+        a.out_f32, a.ldo32 = out_f32.data_ptr(), out_f32.stride(0)
+    _abi.check(lib.gecco_adagn(C.byref(a), _stream(x)))
+    return out_f32, out_bf16
+
+
+def lift(xin: Tensor, w: Tensor, b: Tensor, *, rows_per_cloud: int, sigma: Tensor | None = None, sigma_stride: int = 1,
+         sigma_data: float = 1.0, stats: Tensor | None = None, stat_gs: int = STAT_GS, out: Tensor | None = None) -> Tensor:
+    lib = _lib_for(xin)
+    assert xin.dtype == torch.float32 and xin.is_contiguous() and xin.shape[-1] == 3
+    clouds, n = xin.shape[0], xin.shape[1]
+    c = w.shape[0]
+    if out is None:
+        out = torch.empty((clouds * rows_per_cloud, c), device=xin.device, dtype=torch.float32)
+    a = _abi.LiftArgs()
+    a.xin = xin.data_ptr()
+    a.sigma, a.sigma_stride, a.sigma_data = (0 if sigma is None else sigma.data_ptr()), sigma_stride, sigma_data
+    a.w, a.b = w.data_ptr(), b.data_ptr()
+    a.clouds, a.rows_per_cloud, a.valid_rows, a.c = clouds, rows_per_cloud, n, c
+    a.x, a.ldx = out.data_ptr(), out.stride(0)
+    a.stats, a.stat_gs = (0 if stats is None else stats.data_ptr()), stat_gs
+    _abi.check(lib.gecco_lift(C.byref(a), _stream(xin)))
+    return out
+
+
+def head(x: Tensor, w_out: Tensor, b_out: Tensor, *, clouds: int, rows_per_cloud: int, valid_rows: int, norm: int,
+         groups: int = 16, stats: Tensor | None = None, stat_gs: int = STAT_GS, eps: float = 1e-5,
+         xin: Tensor | None = None, sigma: Tensor | None = None, sigma_stride: int = 1, sigma_data: float = 1.0,
+         mode: int = 0, out: Tensor | None = None, x_hat: Tensor | None = None, x_next: Tensor | None = None,
+         d_cur: Tensor | None = None, xin_next: Tensor | None = None, noise_next: Tensor | None = None,
+         t_hat: float = 0.0, t_next: float = 0.0, churn_next: float = 0.0):
+    lib = _lib_for(x)
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    if mode in (0, 1) and out is None:
+        out = torch.empty((clouds, valid_rows, 3), device=x.device, dtype=torch.float32)
+    a = _abi.HeadArgs()
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    a.clouds, a.rows_per_cloud, a.valid_rows, a.c = clouds, rows_per_cloud, valid_rows, x.shape[1]
+    a.norm, a.groups, a.stats, a.stat_gs, a.eps = norm, groups, (0 if stats is None else stats.data_ptr()), stat_gs, eps
+    a.w_out, a.b_out = w_out.data_ptr(), b_out.data_ptr()
+    a.xin = 0 if xin is None else xin.data_ptr()
+    a.sigma, a.sigma_stride, a.sigma_data = (0 if sigma is None else sigma.data_ptr()), sigma_stride, sigma_data
+    a.mode = mode
+    a.out_f32 = 0 if out is None else out.data_ptr()
+    a.x_hat = 0 if x_hat is None else x_hat.data_ptr()
+    a.x_next = 0 if x_next is None else x_next.data_ptr()
+    a.d_cur = 0 if d_cur is None else d_cur.data_ptr()
+    a.xin_next = 0 if xin_next is None else xin_next.data_ptr()
+    a.noise_next = 0 if noise_next is None else noise_next.data_ptr()
+    a.t_hat, a.t_next, a.churn_next = t_hat, t_next, churn_next
+    _abi.check(lib.gecco_head(C.byref(a), _stream(x)))
+    return out
+
+
+REPARAM_KIND = {"none": 0, "gaussian": 1, "uvl": 2}
+
+
+def reparam(x: Tensor, kind: int, to_data: bool, mean=None, sigma=None, logit_scale: float = 1.1, K: Tensor | None = None) -> Tensor:
+    """reparam.py data_to_diffusion / diffusion_to_data on [B, N, 3] float32 or float64."""
+    lib = _lib_for(x)
+    assert x.dtype in (torch.float32, torch.float64) and x.shape[-1] == 3
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    mean_a = (C.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
+    sig_a = (C.c_float * 3)(*(sigma if sigma is not None else (1.0, 1.0, 1.0)))
+    if K is not None:
+        K = K.to(torch.float32).contiguous()
+    clouds, pts = x.shape[0], x.shape[1]
+    _abi.check(lib.gecco_reparam(_ptr(x), _ptr(out), int(x.dtype == torch.float64), kind, int(to_data), mean_a, sig_a,
+                                 C.c_float(logit_scale), _ptr(K), clouds, pts, _stream(x)))
+    return out
+
+
+def pack_features(f: Tensor) -> Tensor:
+    """fp32 NCHW feature map -> bf16 NHWC (the layout gecco_lookup gathers from)."""
+    lib = _lib_for(f)
+    f = f.to(torch.float32).contiguous()
+    b, c, h, w = f.shape
+    out = torch.empty((b, h, w, c), device=f.device, dtype=torch.bfloat16)
+    _abi.check(lib.gecco_pack_features(_ptr(f), _ptr(out), b, c, h, w, _stream(f)))
+    return out
+
+
+def lookup(xin: Tensor, levels: list[Tensor], K: Tensor, *, reparam_kind: int, mean=None, sigma_r=None,
+           logit_scale: float = 1.1, sigma: Tensor | None = None, sigma_stride: int = 1, sigma_data: float = 1.0,
+           rows_per_cloud: int | None = None, out_bf16: Tensor | bool | None = None, out_f32: Tensor | bool | None = None,
+           stats: Tensor | None = None, stat_groups: int = 16):
+    """levels: bf16 NHWC maps [B, H, W, C]; returns ([B*rows_per_cloud, sum C] fp32, bf16)."""
+    lib = _lib_for(xin)
+    assert xin.dtype == torch.float32 and xin.is_contiguous()
+    clouds, pts = xin.shape[0], xin.shape[1]
+    if rows_per_cloud is None:
+        rows_per_cloud = pts
+    ctot = sum(l.shape[-1] for l in levels)
+    if out_bf16 is True:
+        out_bf16 = torch.zeros((clouds * rows_per_cloud, ctot), device=xin.device, dtype=torch.bfloat16)
+    if out_f32 is True:
+        out_f32 = torch.zeros((clouds * rows_per_cloud, ctot), device=xin.device, dtype=torch.float32)
+    if out_bf16 is False:
+        out_bf16 = None
+    if out_f32 is False:
+        out_f32 = None
+    a = _abi.LookupArgs()
+    a.xin = xin.data_ptr()
+    a.sigma, a.sigma_stride, a.sigma_data = (0 if sigma is None else sigma.data_ptr()), sigma_stride, sigma_data
+    a.reparam = reparam_kind
+    for j in range(3):
+        a.mean[j] = 0.0 if mean is None else float(mean[j])
+        a.sigma_r[j] = 1.0 if sigma_r is None else float(sigma_r[j])
+    a.logit_scale = logit_scale
+    K = K.to(torch.float32).contiguous()
+    a.K = K.data_ptr()
+    a.n_levels = len(levels)
+    for i, l in enumerate(levels):
+        assert l.dtype == torch.bfloat16 and l.is_contiguous() and l.shape[0] == clouds
+        a.level_ptr[i] = l.data_ptr()
+        a.level_h[i], a.level_w[i], a.level_c[i] = l.shape[1], l.shape[2], l.shape[3]
+    a.clouds, a.points, a.rows_per_cloud = clouds, pts, rows_per_cloud
+    if out_bf16 is not None:
+        a.out_bf16, a.ldo16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if out_f32 is not None:
+        a.out_f32, a.ldo32 = out_f32.data_ptr(), out_f32.stride(0)
+    if stats is not None:
+        a.stats, a.stat_groups = stats.data_ptr(), stat_groups
+    _abi.check(lib.gecco_lookup(C.byref(a), _stream(xin)))
+    return out_f32, out_bf16
+
+
+def fold_group_norm(w: Tensor, bias: Tensor, stats: Tensor, count: float, groups: int, eps: float = 1e-5):
+    """GroupNorm(groups, affine=False) -> Linear folded into per-cloud bf16 weights and fp32 biases."""
+    lib = _lib_for(w)
+    c_out, c_in = w.shape
+    clouds = stats.shape[0]
+    wb = torch.empty((clouds * c_out, c_in), device=w.device, dtype=torch.bfloat16)
+    bb = torch.empty((clouds, c_out), device=w.device, dtype=torch.float32)
+    _abi.check(lib.gecco_fold_group_norm(_ptr(w), _ptr(bias), _ptr(stats), C.c_double(count), C.c_float(eps), groups,
+                                         c_in, c_out, clouds, _ptr(wb), C.c_int64(c_in), _ptr(bb), _stream(w)))
+    return wb, bb
+
+
+def pool_attention(kv: Tensor, q_inducers: Tensor, *, clouds: int, rows_per_cloud: int, valid_rows: int, heads: int,
+                   head_dim: int, k_off: int, v_off: int, splits: int = 1, out: Tensor | None = None) -> Tensor:
+    lib = _lib_for(kv)
+    assert kv.dtype == torch.bfloat16 and q_inducers.dtype == torch.bfloat16 and q_inducers.is_contiguous()
+    inducers = q_inducers.shape[1]
+    partial = torch.empty((clouds * heads * splits * inducers * (head_dim + 2),), device=kv.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((clouds * inducers, heads * head_dim), device=kv.device, dtype=torch.bfloat16)
+    a = _abi.PoolArgs()
+    a.kv, a.ld, a.k_off, a.v_off = kv.data_ptr(), kv.stride(0), k_off, v_off
+    a.clouds, a.rows_per_cloud, a.valid_rows = clouds, rows_per_cloud, valid_rows
+    a.heads, a.head_dim, a.inducers = heads, head_dim, inducers
+    a.q_inducers = q_inducers.data_ptr()
+    a.splits, a.partial = splits, partial.data_ptr()
+    a.out_bf16, a.ldo = out.data_ptr(), out.stride(0)
+    _abi.check(lib.gecco_pool_attention(C.byref(a), _stream(kv)))
+    return out
+
+
+def unpool_attention(q: Tensor, khv: Tensor, *, clouds: int, rows_per_cloud: int, heads: int, head_dim: int, v_off: int,
+                     inducers: int = 64, out: Tensor | None = None) -> Tensor:
+    lib = _lib_for(q)
+    assert q.dtype == torch.bfloat16 and khv.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((clouds * rows_per_cloud, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    a = _abi.UnpoolArgs()
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.kv, a.ldkv, a.v_off = khv.data_ptr(), khv.stride(0), v_off
+    a.clouds, a.rows_per_cloud = clouds, rows_per_cloud
+    a.heads, a.head_dim, a.inducers = heads, head_dim, inducers
+    a.out_bf16, a.ldo = out.data_ptr(), out.stride(0)
+    _abi.check(lib.gecco_unpool_attention(C.byref(a), _stream(q)))
+    return out

@@ -47,7 +47,7 @@ int gecco_init(int device);
  * (:90,112), MLP (models/mlp.py:5-39) and img_feature_proj (models/ray.py:52-55).
  * Epilogue, applied in this order on the fp32 accumulator:
  *   + bias[cloud*bias_stride + n]                     (bias may be NULL)
- *   + xyz embed: sum_j c_in(sigma)*geom[m,j]*wx[n,j]  (geom may be NULL; models/ray.py:99,113)
+ *   + xyz embed: sum_j c_in(sigma)*geom[point,j]*wx[n,j]  (geom may be NULL; models/ray.py:99,113)
  *   Gaussian activation (exp(-z^2/(2 alpha^2)) - 0.7)/0.28 when act != 0 (models/activation.py:17-24)
  *   + res[m, n]                                       (res may be NULL; residual adds set_transformer.py:164,166)
  *   per (cloud, 12-channel group) sum / sum of squares of the result added into
@@ -69,12 +69,153 @@ typedef struct gecco_gemm_args {
   float* out_f32;  int64_t ldo32;
   void* out_bf16;  int64_t ldo16;
   double* stats;
-  const float* geom;        /* [M, 3] fp32 raw sampler state x (not yet scaled by c_in) */
-  const float* sigma; int32_t sigma_stride; /* sigma[cloud*sigma_stride] */
+  const float* geom;        /* [clouds, valid_rows, 3] fp32 raw sampler state x (not yet scaled by c_in) */
+  const float* sigma; int32_t sigma_stride; float sigma_data; /* sigma[cloud*sigma_stride] */
   const float* wx;          /* [n_out, 3] fp32 */
 } gecco_gemm_args;
 
 int gecco_gemm(const gecco_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Group statistics: stats[cloud][c / group_size][{sum, sum of squares}] += over the
+ * first valid_rows rows of each cloud (double accumulators, caller zeroes them).
+ * The statistics half of nn.GroupNorm as used by AdaGN (models/normalization.py:21-25,37-38)
+ * and GroupNormBNC (models/ray.py:20-30).
+ * ------------------------------------------------------------------------ */
+int gecco_group_stats(const float* x, int64_t ldx, int32_t clouds, int32_t rows_per_cloud, int32_t valid_rows,
+                      int32_t c, int32_t group_size, double* stats, void* stream);
+
+/* AdaGN apply (models/normalization.py:36-44):
+ *   y[b,n,c] = scale_b(t)[c] * (x[b,n,c] - mean[b,g]) * rstd[b,g] + bias_b(t)[c]
+ * scale(t) = t . scale_w[c,:] + scale_b[c], bias likewise (nn.Linear(ctx_dim, C)).
+ * stats are kept at stat_gs-channel granularity; the normalisation group is c/groups
+ * channels wide (a multiple of stat_gs).  Padding rows are written as zeros. */
+typedef struct gecco_adagn_args {
+  const float* x; int64_t ldx;
+  const double* stats; int32_t stat_gs;
+  const float* t; int32_t t_stride; int32_t ctx_dim;
+  const float* scale_w; const float* scale_b; const float* bias_w; const float* bias_b;
+  int32_t clouds, rows_per_cloud, valid_rows, c, groups;
+  float eps;
+  void* out_bf16; int64_t ldo16;
+  float* out_f32; int64_t ldo32;
+} gecco_adagn_args;
+int gecco_adagn(const gecco_adagn_args* args, void* stream);
+
+/* LinearLift.lift (models/linear_lift.py:21,44) on the EDM-scaled input:
+ *   x[b,n,:] = W (c_in(sigma_b) * xin[b,n,:]) + bias, c_in = 1/sqrt(sigma_data^2 + sigma^2)
+ * (sigma NULL: c_in = 1) and, when stats != NULL, the statistics of x for the first AdaGN. */
+typedef struct gecco_lift_args {
+  const float* xin;                 /* [clouds, valid_rows, 3] */
+  const float* sigma; int32_t sigma_stride; float sigma_data;
+  const float* w; const float* b;   /* [C, 3], [C] */
+  int32_t clouds, rows_per_cloud, valid_rows, c;
+  float* x; int64_t ldx;            /* [clouds*rows_per_cloud, C] */
+  double* stats; int32_t stat_gs;
+} gecco_lift_args;
+int gecco_lift(const gecco_lift_args* args, void* stream);
+
+/* Output head fused with the EDM preconditioning and the sampler update.
+ *   F = W_out . norm(x) + b_out   norm: 0 none, 1 LayerNorm(C) (models/linear_lift.py:26-29),
+ *                                       2 GroupNorm(groups) over points (models/ray.py:56-59)
+ *   mode 0: out_f32 = F
+ *   mode 1: out_f32 = c_skip*xin + c_out*F                               (diffusion.py:46-57)
+ *   mode 2: Euler step   d_cur=(x_hat-D)/t_hat; x_next=x_hat+(t_next-t_hat)d_cur   (diffusion.py:335-336)
+ *   mode 3: Heun step    x = x_hat+(t_next-t_hat)(d_cur/2+d'/2) (diffusion.py:346-347), then the churn
+ *           of the following step x_hat = x + churn_next*noise_next (diffusion.py:323-325)
+ * Sampler state is float64 like the reference; xin_next receives the fp32 input of the next evaluation. */
+typedef struct gecco_head_args {
+  const float* x; int64_t ldx;
+  int32_t clouds, rows_per_cloud, valid_rows, c;
+  int32_t norm, groups; const double* stats; int32_t stat_gs; float eps;
+  const float* w_out; const float* b_out;
+  const float* xin;
+  const float* sigma; int32_t sigma_stride; float sigma_data;
+  int32_t mode;
+  float* out_f32;
+  double* x_hat; double* x_next; double* d_cur; float* xin_next; const float* noise_next;
+  double t_hat, t_next, churn_next;
+} gecco_head_args;
+int gecco_head(const gecco_head_args* args, void* stream);
+
+/* Reparametrisations (reparam.py:31-201): kind 0 NoReparam, 1 GaussianReparam, 2 UVLReparam;
+ * to_data != 0 is diffusion_to_data, else data_to_diffusion.  in/out are [clouds, points, 3]
+ * float (is_double == 0) or double.  mean/sigma are HOST arrays of 3 floats; K is the device
+ * [clouds,3,3] fp32 camera matrix (UVL only). */
+int gecco_reparam(const void* in, void* out, int32_t is_double, int32_t kind, int32_t to_data,
+                  const float* host_mean, const float* host_sigma, float logit_scale, const float* K,
+                  int32_t clouds, int32_t points_per_cloud, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Projective feature lookup: RayNetwork.extract_image_features (models/ray.py:64-87),
+ * i.e. reparam.diffusion_to_data -> kornia project_points -> F.grid_sample(bilinear,
+ * zeros padding, align_corners=False) on every pyramid level -> channel concat.
+ * The input is the raw sampler state; the EDM input scaling c_in(sigma) is applied inside
+ * (sigma NULL: no scaling).  Pyramid levels are bf16 channels-last [clouds, H, W, C]
+ * (see gecco_pack_features).  Output rows [cloud*rows_per_cloud + point, sum C] as bf16
+ * and/or fp32; optional GroupNorm statistics [clouds][stat_groups][2] of the fp32 result
+ * (models/ray.py:53).
+ * ------------------------------------------------------------------------ */
+#define GECCO_MAX_LEVELS 4
+typedef struct gecco_lookup_args {
+  const float* xin;                       /* [clouds, points, 3] */
+  const float* sigma; int32_t sigma_stride; float sigma_data;
+  int32_t reparam;                        /* 0 none, 1 gaussian, 2 uvl */
+  float mean[3]; float sigma_r[3]; float logit_scale;
+  const float* K;                         /* [clouds, 3, 3] */
+  int32_t n_levels;
+  const void* level_ptr[GECCO_MAX_LEVELS];
+  int32_t level_h[GECCO_MAX_LEVELS], level_w[GECCO_MAX_LEVELS], level_c[GECCO_MAX_LEVELS];
+  int32_t clouds, points, rows_per_cloud;
+  void* out_bf16; int64_t ldo16;
+  float* out_f32; int64_t ldo32;
+  double* stats; int32_t stat_groups;
+} gecco_lookup_args;
+int gecco_lookup(const gecco_lookup_args* args, void* stream);
+
+/* nn.Sequential(GroupNormBNC(groups, c_in, affine=False), nn.Linear(c_in, c_out)) (models/ray.py:52-55)
+ * folded into per-cloud weights:  w_folded[cloud][o][c] = w[o][c]*rstd, bias_folded[cloud][o] =
+ * bias[o] - sum_c w[o][c]*mean*rstd, with mean/rstd from stats [clouds][groups][2] over `count` elements. */
+int gecco_fold_group_norm(const float* w, const float* bias, const double* stats, double count, float eps,
+                          int32_t groups, int32_t c_in, int32_t c_out, int32_t clouds, void* w_folded_bf16,
+                          int64_t ldw, float* bias_folded, void* stream);
+
+/* Conditioner hand-off: fp32 NCHW feature map (models/feature_pyramid.py:62-73) -> bf16 NHWC. */
+int gecco_pack_features(const float* nchw, void* nhwc_bf16, int32_t images, int32_t c, int32_t h, int32_t w,
+                        void* stream);
+
+/* ------------------------------------------------------------------------
+ * AttentionPool's scaled_dot_product_attention with the learned inducer queries
+ * (models/set_transformer.py:57-63).  kv holds the bf16 kv_proj output, K of head h at
+ * columns k_off + h*head_dim, V at v_off + h*head_dim ("b n (t h d)" layout, :50-55).
+ * q_inducers: bf16 [heads][64][head_dim] = inducers * (head_dim^-0.5 * log2 e).
+ * The keys are processed in `splits` ranges; partial is scratch of
+ * clouds*heads*splits*64*(head_dim+2) floats.  out: bf16 [clouds*64, heads*head_dim]
+ * ("b h i d -> b i (h d)", :63), the operand of out_proj.
+ * ------------------------------------------------------------------------ */
+typedef struct gecco_pool_args {
+  const void* kv; int64_t ld; int32_t k_off, v_off;
+  int32_t clouds, rows_per_cloud, valid_rows;
+  int32_t heads, head_dim, inducers;
+  const void* q_inducers;
+  int32_t splits; float* partial;
+  void* out_bf16; int64_t ldo;
+} gecco_pool_args;
+int gecco_pool_attention(const gecco_pool_args* args, void* stream);
+
+/* Attention core of Broadcast.unpool = nn.MultiheadAttention(query=points, key=value=inducers)
+ * (models/set_transformer.py:90,112) between the in- and out-projections: per head
+ * softmax(q k^T) v over the 64 inducers.  q: bf16 rows [clouds*rows_per_cloud] with head h at
+ * columns h*head_dim, already multiplied by head_dim^-0.5 * log2 e (folded into the q
+ * projection); kv: bf16 [clouds*64, *] with k at column h*head_dim and v at v_off + h*head_dim. */
+typedef struct gecco_unpool_args {
+  const void* q; int64_t ldq;
+  const void* kv; int64_t ldkv; int32_t v_off;
+  int32_t clouds, rows_per_cloud;
+  int32_t heads, head_dim, inducers;
+  void* out_bf16; int64_t ldo;
+} gecco_unpool_args;
+int gecco_unpool_attention(const gecco_unpool_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,17 +74,19 @@ def test_gemm_act_and_percloud_weights(cuda):
 def test_gemm_xyz_embed(cuda):
     from gecco_b200 import ops
 
-    B, Np, K, C = 2, 128, 128, 192
+    B, N, Np, K, C = 2, 100, 128, 128, 192
     g = torch.Generator(device="cpu").manual_seed(13)
     a = torch.randn(B * Np, K, generator=g).to(cuda).bfloat16()
     w = (torch.randn(C, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
     bias = torch.randn(C, generator=g).to(cuda)
-    geom = torch.randn(B * Np, 3, generator=g).to(cuda)
+    geom = torch.randn(B, N, 3, generator=g).to(cuda)
     wx = torch.randn(C, 3, generator=g).to(cuda)
     sigma = torch.tensor([0.5, 7.0], device=cuda)
-    o32, _ = ops.gemm(a, w, bias=bias, out_f32=True, rows_per_cloud=Np, geom=geom, sigma=sigma, sigma_stride=1, wx=wx)
+    o32, _ = ops.gemm(a, w, bias=bias, out_f32=True, rows_per_cloud=Np, valid_rows=N, geom=geom, sigma=sigma,
+                      sigma_stride=1, wx=wx)
     torch.cuda.synchronize()
     c_in = 1 / (1 + sigma**2).sqrt()
-    gg = geom.view(B, Np, 3) * c_in.view(B, 1, 1)
-    ref = _ref(a, w, bias=bias) + (gg.view(-1, 3) @ wx.t())
-    assert (o32 - ref).abs().max().item() < 2e-3
+    gg = geom * c_in.view(B, 1, 1)
+    ref = _ref(a, w, bias=bias).view(B, Np, C)
+    ref[:, :N] += gg @ wx.t()
+    assert (o32.view(B, Np, C) - ref).abs().max().item() < 2e-3
