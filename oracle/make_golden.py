@@ -1,0 +1,171 @@
+"""Generates tests/golden/*.pt from the UNMODIFIED reference package.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the reference is not available on the GPU box):
+
+    python oracle/make_golden.py
+
+It imports /root/reference/gecco-torch/src/gecco_torch through the import stubs in oracle/stubs/
+(lightning, kornia, h5py, imageio are not installed here; kornia's two projection functions are
+restated in the stub — see oracle/stubs/README.md), builds the reference modules with the reference
+constructors, overwrites their parameters with the seeded synthetic weights of tests/synth.py, runs the
+reference forward / sample_stochastic / upsample on seeded synthetic inputs on CPU in fp32, and stores
+the recipe + outputs.  Weights and inputs are NOT stored: tests regenerate them from the same seeds.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle" / "stubs"))
+sys.path.insert(0, "/root/reference/gecco-torch/src")
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+from gecco_torch.diffusion import Diffusion, EDMLoss, EDMPrecond, IdleConditioner, LogUniformSchedule  # noqa: E402
+from gecco_torch.models.activation import GaussianActivation  # noqa: E402
+from gecco_torch.models.feature_pyramid import FeaturePyramidContext  # noqa: E402
+from gecco_torch.models.linear_lift import LinearLift  # noqa: E402
+from gecco_torch.models.ray import RayNetwork  # noqa: E402
+from gecco_torch.models.set_transformer import SetTransformer  # noqa: E402
+from gecco_torch.reparam import GaussianReparam, UVLReparam  # noqa: E402
+from gecco_torch.structs import Context3d  # noqa: E402
+
+from tests import synth  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+WEIGHT_SEED = 1234
+
+
+class FixedConditioner(torch.nn.Module):
+    """Stands in for ConvNeXtExtractor (models/feature_pyramid.py:28-73): returns a fixed synthetic pyramid.
+    The conditioner is upstream of the hot path; the path under test starts at its output."""
+
+    def __init__(self, features):
+        super().__init__()
+        self.features = features
+
+    def forward(self, raw_ctx):
+        return FeaturePyramidContext(features=self.features, K=raw_ctx.K)
+
+
+def build_reference(kind: str, reparam: str, mean, sigma, sigma_max: float, features=None):
+    st = SetTransformer(n_layers=synth.N_LAYERS, num_inducers=synth.NUM_INDUCERS, feature_dim=synth.FEATURE_DIM,
+                        t_embed_dim=1, num_heads=synth.NUM_HEADS, activation=GaussianActivation)
+    m, s = torch.tensor(mean), torch.tensor(sigma)
+    rp = GaussianReparam(m, s) if reparam == "gaussian" else UVLReparam(m, s)
+    if kind == "uncond":
+        net = LinearLift(inner=st, feature_dim=synth.FEATURE_DIM)
+        cond = IdleConditioner()
+    else:
+        net = RayNetwork(backbone=st, reparam=rp, context_dims=synth.CONTEXT_DIMS)
+        cond = FixedConditioner(features)
+    model = Diffusion(backbone=EDMPrecond(model=net), conditioner=cond, reparam=rp,
+                      loss=EDMLoss(schedule=LogUniformSchedule(max=sigma_max)))
+    sd = synth.full_state_dict(kind, reparam, mean, sigma, WEIGHT_SEED)
+    ref_sd = model.state_dict()
+    # the synthetic schema must be exactly the reference's learnable schema
+    assert set(ref_sd) == set(sd), (sorted(set(ref_sd) ^ set(sd)))
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+def sub(t: torch.Tensor) -> torch.Tensor:
+    """strided sub-sample of an inducer state [B, 64, C] (keeps fixtures small)"""
+    return t[:, ::8, ::8].contiguous()
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    OUT.mkdir(parents=True, exist_ok=True)
+    recipe_common = dict(weight_seed=WEIGHT_SEED, feature_dim=synth.FEATURE_DIM, n_layers=synth.N_LAYERS,
+                         num_heads=synth.NUM_HEADS, num_inducers=synth.NUM_INDUCERS, torch=torch.__version__)
+
+    # ---------------------------------------------------------------- unconditional (config 1)
+    kind, rp = "uncond", "gaussian"
+    cfg = dict(kind=kind, reparam=rp, **synth.UNCOND_REPARAM, sigma_max=165.0)
+    model = build_reference(kind, rp, cfg["mean"], cfg["sigma"], cfg["sigma_max"])
+    B, N = 2, 300
+    x = torch.randn(B, N, 3, generator=synth.gen(11)) * 3
+    sig = torch.tensor([0.05, 7.0])
+    with torch.no_grad():
+        D, hs = model(x, sig, None, do_cache=True)
+        D_plain = model(x, sig, None)
+        assert torch.equal(D, D_plain)
+        x2 = torch.randn(B, 200, 3, generator=synth.gen(12)) * 3
+        D_cached = model(x2, sig, None, cache=hs)
+        samp = model.sample_stochastic((2, 256, 3), None, rng=synth.gen(42), num_steps=6)
+        ts = model.t_steps(64, 165.0, 0.002, 7)
+    torch.save(dict(recipe={**recipe_common, **cfg, "x_seed": 11, "x_scale": 3.0, "B": B, "N": N, "noise_sigma": sig,
+                            "x2_seed": 12, "N2": 200, "sample_shape": (2, 256, 3), "sample_seed": 42, "sample_steps": 6},
+                    D=D, hs_sub=[sub(h) for h in hs], D_cached=D_cached, sample=samp, t_steps=ts),
+               OUT / "uncond.pt")
+    print("uncond", D.abs().mean().item(), samp.abs().mean().item())
+
+    # ---------------------------------------------------------------- conditional, GaussianReparam (config 2)
+    kind, rp = "cond", "gaussian"
+    cfg = dict(kind=kind, reparam=rp, **synth.SHAPENET_VOL_REPARAM, sigma_max=165.0)
+    B, N = 2, 333
+    feats = synth.synth_features(B, (34, 17, 8), 21)
+    K = synth.camera(B, synth.K_SHAPENET)
+    ctx = Context3d(image=torch.zeros(B, 3, 137, 137), K=K)
+    model = build_reference(kind, rp, cfg["mean"], cfg["sigma"], cfg["sigma_max"], feats)
+    x = torch.randn(B, N, 3, generator=synth.gen(22)) * 2
+    sig = torch.tensor([0.3, 40.0])
+    with torch.no_grad():
+        D = model(x, sig, ctx)
+        c_in = 1 / (1 + sig**2).sqrt()
+        look = model.backbone.model.extract_image_features(x * c_in[:, None, None], feats, ctx)
+        samp = model.sample_stochastic((2, 200, 3), ctx, rng=synth.gen(43), num_steps=5)
+    torch.save(dict(recipe={**recipe_common, **cfg, "K": synth.K_SHAPENET, "feat_sizes": (34, 17, 8), "feat_seed": 21,
+                            "x_seed": 22, "x_scale": 2.0, "B": B, "N": N, "noise_sigma": sig,
+                            "sample_shape": (2, 200, 3), "sample_seed": 43, "sample_steps": 5},
+                    D=D, lookup_sub=look[:, ::3].contiguous(), sample=samp),
+               OUT / "cond_gaussian.pt")
+    print("cond_gaussian", D.abs().mean().item(), look.abs().mean().item(), samp.abs().mean().item())
+
+    # ---------------------------------------------------------------- conditional, UVLReparam (configs 3, 4)
+    kind, rp = "cond", "uvl"
+    cfg = dict(kind=kind, reparam=rp, **synth.UVL_REPARAM, sigma_max=180.0)
+    B, N = 2, 256
+    feats = synth.synth_features(B, (64, 32, 16), 31)
+    K = synth.camera(B, synth.K_TASKONOMY)
+    ctx = Context3d(image=torch.zeros(B, 3, 256, 256), K=K)
+    model = build_reference(kind, rp, cfg["mean"], cfg["sigma"], cfg["sigma_max"], feats)
+    x = torch.randn(B, N, 3, generator=synth.gen(32)) * 1.5
+    sig = torch.tensor([0.002, 180.0])
+    with torch.no_grad():
+        D, hs = model(x, sig, ctx, do_cache=True)
+        c_in = 1 / (1 + sig**2).sqrt()
+        look = model.backbone.model.extract_image_features(x * c_in[:, None, None], feats, ctx)
+        x2 = torch.randn(B, 500, 3, generator=synth.gen(33)) * 1.5
+        D_cached = model(x2, sig, ctx, cache=hs)
+        samp = model.sample_stochastic((2, 192, 3), ctx, rng=synth.gen(44), num_steps=5)
+        # reparam round trip on in-frustum data
+        diff = torch.randn(B, 64, 3, generator=synth.gen(34))
+        data = model.reparam.diffusion_to_data(diff, ctx)
+        back = model.reparam.data_to_diffusion(data, ctx)
+        # upsample (diffusion.py:354-470): seed cloud in data space, in frustum
+        seed_cloud = model.reparam.diffusion_to_data(torch.randn(B, 128, 3, generator=synth.gen(35)), ctx)
+        ups = model.upsample(seed_cloud, n_new=384, context=ctx, seed=7, num_substeps=2, num_steps=3)
+    torch.save(dict(recipe={**recipe_common, **cfg, "K": synth.K_TASKONOMY, "feat_sizes": (64, 32, 16), "feat_seed": 31,
+                            "x_seed": 32, "x_scale": 1.5, "B": B, "N": N, "noise_sigma": sig, "x2_seed": 33, "N2": 500,
+                            "sample_shape": (2, 192, 3), "sample_seed": 44, "sample_steps": 5,
+                            "rt_seed": 34, "ups_seed_cloud_seed": 35, "ups_n_seed": 128, "ups_n_new": 384,
+                            "ups_seed": 7, "ups_substeps": 2, "ups_steps": 3},
+                    D=D, hs_sub=[sub(h) for h in hs], lookup_sub=look[:, ::3].contiguous(), D_cached=D_cached,
+                    sample=samp, rt_data=data, rt_back=back, upsample=ups),
+               OUT / "cond_uvl.pt")
+    print("cond_uvl", D.abs().mean().item(), look.abs().mean().item(), samp.abs().mean().item(), ups.abs().mean().item(),
+          (back - diff).abs().max().item())
+    for f in sorted(OUT.glob("*.pt")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Pins the CPU oracle (oracle/gecco_oracle.py) against the golden vectors minted from the UNMODIFIED
+reference package by oracle/make_golden.py (the reference ships no tests of its own)."""
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import gecco_oracle as O
+from tests import synth
+
+GOLD = Path(__file__).parent / "golden"
+TOL = 2e-5  # fp32 re-association only
+
+
+def load(name):
+    g = torch.load(GOLD / name, weights_only=False)
+    r = g["recipe"]
+    cfg = O.OracleConfig(kind=r["kind"], reparam=r["reparam"], sigma_max=r["sigma_max"], n_layers=r["n_layers"],
+                         num_heads=r["num_heads"])
+    sd = synth.full_state_dict(r["kind"], r["reparam"], r["mean"], r["sigma"], r["weight_seed"])
+    return g, r, cfg, sd
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def test_uncond_denoise_cache_sample():
+    g, r, cfg, sd = load("uncond.pt")
+    x = torch.randn(r["B"], r["N"], 3, generator=synth.gen(r["x_seed"])) * r["x_scale"]
+    D, hs = O.denoise(cfg, sd, x, r["noise_sigma"], return_h=True)
+    assert rel(D, g["D"]) < TOL
+    for h, hg in zip(hs, g["hs_sub"]):
+        assert rel(h[:, ::8, ::8], hg) < TOL
+    x2 = torch.randn(r["B"], r["N2"], 3, generator=synth.gen(r["x2_seed"])) * r["x_scale"]
+    assert rel(O.denoise(cfg, sd, x2, r["noise_sigma"], hs=hs), g["D_cached"]) < TOL
+    s = O.sample_stochastic(cfg, sd, r["sample_shape"], rng=synth.gen(r["sample_seed"]), num_steps=r["sample_steps"])
+    assert s.dtype == torch.float64
+    assert rel(s, g["sample"]) < 1e-4
+    assert torch.equal(O.t_steps(64, 165.0, 0.002, 7), g["t_steps"])
+
+
+def test_cond_gaussian():
+    g, r, cfg, sd = load("cond_gaussian.pt")
+    feats = synth.synth_features(r["B"], r["feat_sizes"], r["feat_seed"])
+    K = synth.camera(r["B"], r["K"])
+    x = torch.randn(r["B"], r["N"], 3, generator=synth.gen(r["x_seed"])) * r["x_scale"]
+    assert rel(O.denoise(cfg, sd, x, r["noise_sigma"], feats, K), g["D"]) < TOL
+    c_in = 1 / (1 + r["noise_sigma"] ** 2).sqrt()
+    look = O.extract_image_features(cfg, sd, x * c_in[:, None, None], feats, K)
+    assert rel(look[:, ::3], g["lookup_sub"]) < TOL
+    s = O.sample_stochastic(cfg, sd, r["sample_shape"], feats, K, rng=synth.gen(r["sample_seed"]), num_steps=r["sample_steps"])
+    assert rel(s, g["sample"]) < 1e-4
+
+
+def test_cond_uvl_cache_upsample_roundtrip():
+    g, r, cfg, sd = load("cond_uvl.pt")
+    feats = synth.synth_features(r["B"], r["feat_sizes"], r["feat_seed"])
+    K = synth.camera(r["B"], r["K"])
+    x = torch.randn(r["B"], r["N"], 3, generator=synth.gen(r["x_seed"])) * r["x_scale"]
+    D, hs = O.denoise(cfg, sd, x, r["noise_sigma"], feats, K, return_h=True)
+    assert rel(D, g["D"]) < TOL
+    for h, hg in zip(hs, g["hs_sub"]):
+        assert rel(h[:, ::8, ::8], hg) < TOL
+    c_in = 1 / (1 + r["noise_sigma"] ** 2).sqrt()
+    look = O.extract_image_features(cfg, sd, x * c_in[:, None, None], feats, K)
+    assert rel(look[:, ::3], g["lookup_sub"]) < TOL
+    x2 = torch.randn(r["B"], r["N2"], 3, generator=synth.gen(r["x2_seed"])) * r["x_scale"]
+    assert rel(O.denoise(cfg, sd, x2, r["noise_sigma"], feats, K, hs=hs), g["D_cached"]) < TOL
+    diff = torch.randn(r["B"], 64, 3, generator=synth.gen(r["rt_seed"]))
+    data = O.diffusion_to_data(cfg, sd, diff, K)
+    assert rel(data, g["rt_data"]) < TOL
+    assert rel(O.data_to_diffusion(cfg, sd, data, K), g["rt_back"]) < 1e-4
+    # samples are compared in diffusion space: data space goes through exp() of the depth coordinate
+    s = O.sample_stochastic(cfg, sd, r["sample_shape"], feats, K, rng=synth.gen(r["sample_seed"]), num_steps=r["sample_steps"])
+    to_diff = lambda d: O.data_to_diffusion(cfg, sd, d, K.double())
+    assert rel(to_diff(s), to_diff(g["sample"])) < 2e-4
+    seed_cloud = O.diffusion_to_data(cfg, sd, torch.randn(r["B"], r["ups_n_seed"], 3, generator=synth.gen(r["ups_seed_cloud_seed"])), K)
+    u = O.upsample(cfg, sd, seed_cloud, n_new=r["ups_n_new"], features=feats, K=K, seed=r["ups_seed"],
+                   num_substeps=r["ups_substeps"], num_steps=r["ups_steps"])
+    assert rel(to_diff(u), to_diff(g["upsample"])) < 2e-4
+
+
+def test_upsample_argument_check():
+    g, r, cfg, sd = load("uncond.pt")
+    with pytest.raises(ValueError):  # diffusion.py:398-401
+        O.upsample(cfg, sd, torch.zeros(1, 8, 3))
