@@ -118,6 +118,63 @@ class UnpoolArgs(C.Structure):
     ]
 
 
+MAX_LAYERS = 32
+NW_COUNT = 6
+LW_COUNT = 33
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("n_layers", C.c_int32), ("feature_dim", C.c_int32), ("num_heads", C.c_int32), ("num_inducers", C.c_int32),
+        ("mlp_hidden", C.c_int32),
+        ("adagn_groups", C.c_int32),
+        ("head_norm", C.c_int32),
+        ("head_groups", C.c_int32),
+        ("img_groups", C.c_int32),
+        ("n_levels", C.c_int32), ("level_c", C.c_int32 * MAX_LEVELS),
+        ("reparam", C.c_int32),
+        ("mean", C.c_float * 3), ("sigma", C.c_float * 3), ("logit_scale", C.c_float),
+        ("sigma_data", C.c_float),
+    ]
+
+
+class Context(C.Structure):
+    _fields_ = [
+        ("level_ptr", C.c_void_p * MAX_LEVELS),
+        ("level_h", C.c_int32 * MAX_LEVELS), ("level_w", C.c_int32 * MAX_LEVELS),
+        ("K", C.c_void_p),
+    ]
+
+
+class DenoiseArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("sigma", C.c_void_p), ("sigma_stride", C.c_int32), ("sigma_imm", C.c_float),
+        ("t_embed", C.c_void_p), ("t_stride", C.c_int32),
+        ("clouds", C.c_int32), ("points", C.c_int32),
+        ("ctx", Context),
+        ("cache_in", C.c_void_p), ("cache_out", C.c_void_p),
+        ("mode", C.c_int32),
+        ("out", C.c_void_p),
+        ("x_hat", C.c_void_p), ("x_next", C.c_void_p), ("d_cur", C.c_void_p), ("xin_next", C.c_void_p),
+        ("noise_next", C.c_void_p),
+        ("t_hat", C.c_double), ("t_next", C.c_double), ("churn_next", C.c_double),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [
+        ("clouds", C.c_int32), ("points", C.c_int32), ("num_steps", C.c_int32),
+        ("host_t_steps", C.POINTER(C.c_double)), ("host_gamma", C.POINTER(C.c_double)), ("s_noise", C.c_double),
+        ("latents", C.c_void_p), ("noise", C.c_void_p),
+        ("ctx", Context),
+        ("x_out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -140,6 +197,13 @@ def load() -> C.CDLL:
     lib = C.CDLL(str(_LIB_PATH))
     lib.gecco_last_error.restype = C.c_char_p
     lib.gecco_abi_version.restype = C.c_int
+    lib.gecco_workspace_bytes.restype = C.c_int64
+    lib.gecco_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.gecco_launch_count.restype = C.c_int64
+    lib.gecco_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gecco_destroy.argtypes = [C.c_void_p]
+    lib.gecco_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gecco_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

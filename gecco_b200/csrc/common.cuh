@@ -16,10 +16,14 @@ inline int fail_cuda(cudaError_t e, const char* what) {
   return GECCO_ERR_CUDA;
 }
 
+// Counts kernel launches issued through the library on this thread (gecco_launch_count).
+extern thread_local long long g_launches;
+
 #define GECCO_CHECK_LAUNCH(what)                              \
   do {                                                        \
     cudaError_t e__ = cudaGetLastError();                     \
     if (e__ != cudaSuccess) return gecco::fail_cuda(e__, what); \
+    ++gecco::g_launches;                                      \
   } while (0)
 
 #define GECCO_REQUIRE(cond, ...)        \

@@ -29,7 +29,15 @@ int sm_count() {
 
 int resolve_driver();
 
+thread_local long long g_launches = 0;
+
 }  // namespace gecco
+
+extern "C" int64_t gecco_launch_count(int32_t reset) {
+  const long long n = gecco::g_launches;
+  if (reset) gecco::g_launches = 0;
+  return n;
+}
 
 extern "C" int gecco_abi_version(void) { return GECCO_ABI_VERSION; }
 

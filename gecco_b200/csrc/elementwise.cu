@@ -265,7 +265,10 @@ head_kernel(const gecco_head_args a) {
           const double xn = a.x_next[idx];
           const double d_prime = (xn - static_cast<double>(D)) / a.t_next;
           double xnew = xh + (a.t_next - a.t_hat) * (0.5 * a.d_cur[idx] + 0.5 * d_prime);
-          if (a.noise_next != nullptr) xnew = xnew + a.churn_next * static_cast<double>(a.noise_next[idx]);
+          // the reference multiplies the 0-dim float64 churn factor into the fp32 noise tensor, which torch
+          // evaluates in fp32 (diffusion.py:325)
+          if (a.noise_next != nullptr)
+            xnew = xnew + static_cast<double>(__fmul_rn(static_cast<float>(a.churn_next), a.noise_next[idx]));
           a.x_hat[idx] = xnew;
           a.xin_next[idx] = static_cast<float>(xnew);
         }
@@ -280,7 +283,7 @@ __global__ void sampler_init_kernel(const float* __restrict__ latents, const flo
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double x = static_cast<double>(latents[i]) * t0;
-  if (noise != nullptr) x = x + churn * static_cast<double>(noise[i]);
+  if (noise != nullptr) x = x + static_cast<double>(__fmul_rn(static_cast<float>(churn), noise[i]));  // fp32 product, see head_kernel
   x_hat[i] = x;
   xin[i] = static_cast<float>(x);
 }

@@ -1,0 +1,542 @@
+// Denoiser engine: sequences the kernels of one EDM-preconditioned SetTransformer evaluation
+// (Diffusion.forward, diffusion.py:233-247) and the stochastic sampler loop around it
+// (Diffusion.sample_stochastic, diffusion.py:305-347) on one stream.  No host synchronisation, no
+// allocation after gecco_create: everything is CUDA-graph capturable.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+struct gecco_engine {
+  gecco_model_desc d;
+  int device;
+  // fp32 tensors used in place (owned by the caller)
+  const float* net[GECCO_NW_COUNT];
+  std::vector<const float*> lw;  // [n_layers * GECCO_LW_COUNT]
+  // packed (owned)
+  struct Layer {
+    __nv_bfloat16 *pool_kv_w, *pool_out_w, *bmlp_w0, *bmlp_w2, *q_w, *kv_w, *out_w, *mlp_w0, *mlp_w2, *q_ind;
+    float* q_b;
+    float bmlp_alpha, mlp_alpha;
+  };
+  std::vector<Layer> layers;
+  float* img_bias;  // img_feature_proj.1.bias + xyz_embed.bias (cond)
+  void* arena;      // one allocation holding all packed tensors
+  size_t arena_bytes;
+};
+
+namespace gecco {
+
+namespace {
+
+__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i] * scale);
+}
+__global__ void scale_add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst,
+                                     int n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a[i] * scale + (b ? b[i] : 0.f);
+}
+
+// Per evaluation: zero the statistics accumulators, materialise sigma per cloud and c_noise = ln(sigma)/4
+// (diffusion.py:51).
+// Network-level calls pass the embedding directly (t_embed) and an input that is already scaled: sigma_eff = 0
+// makes every c_in(sigma) in the downstream kernels equal to 1 / sigma_data, which the engine cancels by
+// running them with sigma_data = 1.
+__global__ void prep_kernel(double* __restrict__ stats, long long n_stats, const float* __restrict__ sigma, int stride,
+                            float sigma_imm, const float* __restrict__ t_embed, int t_stride, int clouds,
+                            float* __restrict__ sigma_eff, float* __restrict__ c_noise) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long j = i; j < n_stats; j += (long long)gridDim.x * blockDim.x) stats[j] = 0.0;
+  if (i < clouds) {
+    if (t_embed != nullptr) {
+      sigma_eff[i] = 0.f;
+      c_noise[i] = t_embed[(long long)i * t_stride];
+    } else {
+      const float s = sigma ? sigma[(long long)i * stride] : sigma_imm;
+      sigma_eff[i] = s;
+      c_noise[i] = logf(s) / 4.0f;
+    }
+  }
+}
+
+__global__ void copy_f64_kernel(const double* __restrict__ src, double* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off = align_up(off + count * sizeof(T));
+    return p;
+  }
+};
+
+struct Workspace {
+  int Np, rows, irows, splits;
+  float* x;            // [rows, C] residual stream
+  __nv_bfloat16* y;    // [rows, C] normalised operand / attention output
+  __nv_bfloat16* big;  // [rows, max(2C, hidden, sum level_c)] kv | mlp hidden | looked-up image features
+  __nv_bfloat16* q;    // [rows, C]
+  __nv_bfloat16 *pooled, *hn, *hh, *h3, *khv;
+  float *h, *h2, *partial;
+  double* stats;
+  long long n_stats;
+  float *sigma_eff, *c_noise;
+  __nv_bfloat16* wfold;
+  float* bfold;
+  double *x_hat, *x_next, *d_cur;
+  float *xin_a, *xin_b;
+  size_t bytes;
+};
+
+int pool_splits(int clouds, int heads, int n_tiles) {
+  int s = ceil_div(8 * 148, clouds * heads);
+  if (s < 1) s = 1;
+  if (s > n_tiles) s = n_tiles;
+  return s;
+}
+
+Workspace carve(const gecco_engine* e, int clouds, int points, void* base) {
+  const gecco_model_desc& d = e->d;
+  Workspace w;
+  const int C = d.feature_dim, I = d.num_inducers, hid = d.mlp_hidden;
+  int ctx = 0;
+  for (int l = 0; l < d.n_levels; ++l) ctx += d.level_c[l];
+  w.Np = ceil_div(points, 128) * 128;
+  w.rows = clouds * w.Np;
+  w.irows = clouds * I;
+  w.splits = pool_splits(clouds, d.num_heads, ceil_div(points, 64));
+  int wide = 2 * C;
+  if (hid > wide) wide = hid;
+  if (ctx > wide) wide = ctx;
+  Carver c{static_cast<uint8_t*>(base)};
+  w.x = c.take<float>((size_t)w.rows * C);
+  w.y = c.take<__nv_bfloat16>((size_t)w.rows * C);
+  w.big = c.take<__nv_bfloat16>((size_t)w.rows * wide);
+  w.q = c.take<__nv_bfloat16>((size_t)w.rows * C);
+  w.pooled = c.take<__nv_bfloat16>((size_t)w.irows * C);
+  w.hn = c.take<__nv_bfloat16>((size_t)w.irows * C);
+  w.hh = c.take<__nv_bfloat16>((size_t)w.irows * hid);
+  w.h3 = c.take<__nv_bfloat16>((size_t)w.irows * C);
+  w.khv = c.take<__nv_bfloat16>((size_t)w.irows * 2 * C);
+  w.h = c.take<float>((size_t)w.irows * C);
+  w.h2 = c.take<float>((size_t)w.irows * C);
+  w.partial = c.take<float>((size_t)clouds * d.num_heads * w.splits * I * (C / d.num_heads + 2));
+  // statistics at 12-channel (= C / adagn_groups) granularity: per layer {broadcast_norm, norm_1, norm_2, mlp_norm},
+  // plus the head norm, plus the image-feature GroupNorm
+  const int sg = d.adagn_groups;
+  w.n_stats = (long long)clouds * ((4LL * d.n_layers + 1) * sg * 2 + (d.kind == 1 ? d.img_groups * 2 : 0));
+  w.stats = c.take<double>((size_t)w.n_stats);
+  w.sigma_eff = c.take<float>(clouds);
+  w.c_noise = c.take<float>(clouds);
+  if (d.kind == 1) {
+    w.wfold = c.take<__nv_bfloat16>((size_t)clouds * C * ctx);
+    w.bfold = c.take<float>((size_t)clouds * C);
+  } else {
+    w.wfold = nullptr;
+    w.bfold = nullptr;
+  }
+  const size_t n3 = (size_t)clouds * points * 3;
+  w.x_hat = c.take<double>(n3);
+  w.x_next = c.take<double>(n3);
+  w.d_cur = c.take<double>(n3);
+  w.xin_a = c.take<float>(n3);
+  w.xin_b = c.take<float>(n3);
+  w.bytes = c.off;
+  return w;
+}
+
+gecco_gemm_args gemm_base(const void* a, long long lda, const void* wgt, long long ldw, int m, int n, int k,
+                          int rows_per_cloud, int valid_rows) {
+  gecco_gemm_args g = {};
+  g.a = a; g.lda = lda; g.w = wgt; g.ldw = ldw;
+  g.m = m; g.n_out = n; g.k = k;
+  g.rows_per_cloud = rows_per_cloud; g.valid_rows = valid_rows;
+  g.sigma_data = 1.f;
+  return g;
+}
+
+gecco_adagn_args adagn_base(const gecco_engine* e, const float* const* nw /* 4 pointers */, const float* x, const double* stats,
+                            const float* t, int clouds, int rows_per_cloud, int valid_rows) {
+  gecco_adagn_args a = {};
+  const int C = e->d.feature_dim;
+  a.x = x; a.ldx = C;
+  a.stats = stats; a.stat_gs = C / e->d.adagn_groups;
+  a.t = t; a.t_stride = 1; a.ctx_dim = 1;
+  a.scale_w = nw[0]; a.scale_b = nw[1]; a.bias_w = nw[2]; a.bias_b = nw[3];
+  a.clouds = clouds; a.rows_per_cloud = rows_per_cloud; a.valid_rows = valid_rows; a.c = C;
+  a.groups = e->d.adagn_groups;
+  a.eps = 1e-5f;
+  return a;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// One evaluation.  `xin` is the raw (un-scaled) [clouds, points, 3] input; the head arguments select what is
+// produced (see gecco_head_args modes).
+int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float* sigma, int sigma_stride, float sigma_imm,
+             const float* t_embed, int t_stride, int clouds, int points, const gecco_context& ctx, const float* cache_in, float* cache_out,
+             gecco_head_args head, cudaStream_t s) {
+  const gecco_model_desc& d = e->d;
+  const int C = d.feature_dim, I = d.num_inducers, H = d.num_heads, hid = d.mlp_hidden, hd = C / H;
+  const int sg = d.adagn_groups, Np = w.Np, rows = w.rows, irows = w.irows;
+  const long long per_norm = (long long)clouds * sg * 2;
+  const float sigma_data = t_embed ? 1.f : d.sigma_data;
+  auto stat = [&](int layer, int which) { return w.stats + ((long long)layer * 4 + which) * per_norm; };
+  double* head_stats = w.stats + 4LL * d.n_layers * per_norm;
+  double* img_stats = head_stats + per_norm;
+
+  {
+    const int threads = 256;
+    long long need = w.n_stats > clouds ? w.n_stats : clouds;
+    int blocks = (int)((need + threads - 1) / threads);
+    if (blocks > 1024) blocks = 1024;
+    if ((long long)blocks * threads < clouds) blocks = ceil_div(clouds, threads);
+    prep_kernel<<<blocks, threads, 0, s>>>(w.stats, w.n_stats, sigma, sigma_stride, sigma_imm, t_embed, t_stride, clouds,
+                                           w.sigma_eff, w.c_noise);
+    GECCO_CHECK_LAUNCH("prep_kernel");
+  }
+
+  // ---------------------------------------------------------------- input embedding
+  if (d.kind == 0) {  // LinearLift.lift (models/linear_lift.py:44)
+    gecco_lift_args a = {};
+    a.xin = xin; a.sigma = w.sigma_eff; a.sigma_stride = 1; a.sigma_data = sigma_data;
+    a.w = e->net[GECCO_NW_EMBED_W]; a.b = e->net[GECCO_NW_EMBED_B];
+    a.clouds = clouds; a.rows_per_cloud = Np; a.valid_rows = points; a.c = C;
+    a.x = w.x; a.ldx = C;
+    a.stats = stat(0, 0); a.stat_gs = C / sg;
+    TRY(launch_lift(a, s));
+  } else {  // RayNetwork: xyz_embed + img_feature_proj(lookup) (models/ray.py:99-113)
+    int ctot = 0;
+    gecco_lookup_args a = {};
+    a.xin = xin; a.sigma = w.sigma_eff; a.sigma_stride = 1; a.sigma_data = sigma_data;
+    a.reparam = d.reparam;
+    for (int j = 0; j < 3; ++j) { a.mean[j] = d.mean[j]; a.sigma_r[j] = d.sigma[j]; }
+    a.logit_scale = d.logit_scale;
+    a.K = ctx.K;
+    a.n_levels = d.n_levels;
+    for (int l = 0; l < d.n_levels; ++l) {
+      a.level_ptr[l] = ctx.level_ptr[l]; a.level_h[l] = ctx.level_h[l]; a.level_w[l] = ctx.level_w[l];
+      a.level_c[l] = d.level_c[l];
+      ctot += d.level_c[l];
+    }
+    a.clouds = clouds; a.points = points; a.rows_per_cloud = Np;
+    a.out_bf16 = w.big; a.ldo16 = ctot;
+    a.stats = img_stats; a.stat_groups = d.img_groups;
+    TRY(launch_lookup(a, s));
+    TRY(launch_fold_gn(e->net[GECCO_NW_IMG_W], e->img_bias, img_stats, (double)points * (ctot / d.img_groups), 1e-5f,
+                       d.img_groups, ctot, C, clouds, w.wfold, ctot, w.bfold, s));
+    gecco_gemm_args g = gemm_base(w.big, ctot, w.wfold, ctot, rows, C, ctot, Np, points);
+    g.w_rows_per_cloud = C;
+    g.bias = w.bfold; g.bias_stride = C;
+    g.geom = xin; g.sigma = w.sigma_eff; g.sigma_stride = 1; g.sigma_data = sigma_data;
+    g.wx = e->net[GECCO_NW_EMBED_W];
+    g.out_f32 = w.x; g.ldo32 = C;
+    g.stats = stat(0, 0);
+    TRY(launch_gemm(g, s));
+  }
+
+  // ---------------------------------------------------------------- SetTransformer (models/set_transformer.py:198-216)
+  for (int l = 0; l < d.n_layers; ++l) {
+    const gecco_engine::Layer& L = e->layers[l];
+    const float* const* lw = e->lw.data() + (size_t)l * GECCO_LW_COUNT;
+    // y = AdaGN_bn(x, t)  (:162)
+    {
+      gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_BN, w.x, stat(l, 0), w.c_noise, clouds, Np, points);
+      a.out_bf16 = w.y; a.ldo16 = C;
+      TRY(launch_adagn(a, s));
+    }
+    if (cache_in == nullptr) {
+      // AttentionPool (:47-65)
+      gecco_gemm_args g = gemm_base(w.y, C, L.pool_kv_w, C, rows, 2 * C, C, Np, points);
+      g.out_bf16 = w.big; g.ldo16 = 2 * C;
+      TRY(launch_gemm(g, s));
+      gecco_pool_args p = {};
+      p.kv = w.big; p.ld = 2 * C; p.k_off = 0; p.v_off = C;
+      p.clouds = clouds; p.rows_per_cloud = Np; p.valid_rows = points;
+      p.heads = H; p.head_dim = hd; p.inducers = I;
+      p.q_inducers = L.q_ind;
+      p.splits = w.splits; p.partial = w.partial;
+      p.out_bf16 = w.pooled; p.ldo = C;
+      TRY(launch_pool_attention(p, s));
+      g = gemm_base(w.pooled, C, L.pool_out_w, C, irows, C, C, I, I);
+      g.out_f32 = w.h; g.ldo32 = C; g.stats = stat(l, 1);
+      TRY(launch_gemm(g, s));
+      // h = norm_2(mlp(norm_1(h)))  (:108-110)
+      gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_N1, w.h, stat(l, 1), w.c_noise, clouds, I, I);
+      a.out_bf16 = w.hn; a.ldo16 = C;
+      TRY(launch_adagn(a, s));
+      g = gemm_base(w.hn, C, L.bmlp_w0, C, irows, hid, C, I, I);
+      g.bias = lw[GECCO_LW_BMLP_B0]; g.act = 1; g.act_alpha = L.bmlp_alpha;
+      g.out_bf16 = w.hh; g.ldo16 = hid;
+      TRY(launch_gemm(g, s));
+      g = gemm_base(w.hh, hid, L.bmlp_w2, hid, irows, C, hid, I, I);
+      g.bias = lw[GECCO_LW_BMLP_B2];
+      g.out_f32 = w.h2; g.ldo32 = C; g.stats = stat(l, 2);
+      TRY(launch_gemm(g, s));
+      a = adagn_base(e, lw + GECCO_LW_N2, w.h2, stat(l, 2), w.c_noise, clouds, I, I);
+      a.out_bf16 = w.h3; a.ldo16 = C;
+      if (cache_out != nullptr) { a.out_f32 = cache_out + (size_t)l * irows * C; a.ldo32 = C; }
+      TRY(launch_adagn(a, s));
+    } else {
+      const long long n = (long long)irows * C;
+      pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cache_in + (size_t)l * irows * C, w.h3, n, 1.0f);
+      GECCO_CHECK_LAUNCH("pack_bf16_kernel(cache)");
+    }
+    // unpool = nn.MultiheadAttention(query=y, key=value=h)  (:112)
+    {
+      gecco_gemm_args g = gemm_base(w.h3, C, L.kv_w, C, irows, 2 * C, C, I, I);
+      g.bias = lw[GECCO_LW_UNPOOL_IN_B] + C;
+      g.out_bf16 = w.khv; g.ldo16 = 2 * C;
+      TRY(launch_gemm(g, s));
+      g = gemm_base(w.y, C, L.q_w, C, rows, C, C, Np, points);
+      g.bias = L.q_b;
+      g.out_bf16 = w.q; g.ldo16 = C;
+      TRY(launch_gemm(g, s));
+      gecco_unpool_args u = {};
+      u.q = w.q; u.ldq = C; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
+      u.clouds = clouds; u.rows_per_cloud = Np; u.heads = H; u.head_dim = hd; u.inducers = I;
+      u.out_bf16 = w.y; u.ldo = C;
+      TRY(launch_unpool_attention(u, s));
+      // x = x + out_proj(attn)  (:164), statistics for mlp_norm
+      g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);
+      g.bias = lw[GECCO_LW_UNPOOL_OUT_B];
+      g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
+      g.stats = stat(l, 3);
+      TRY(launch_gemm(g, s));
+    }
+    // x = x + mlp(AdaGN_mlp(x, t))  (:165-166), statistics for the next broadcast_norm / the head norm
+    {
+      gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_MN, w.x, stat(l, 3), w.c_noise, clouds, Np, points);
+      a.out_bf16 = w.y; a.ldo16 = C;
+      TRY(launch_adagn(a, s));
+      gecco_gemm_args g = gemm_base(w.y, C, L.mlp_w0, C, rows, hid, C, Np, points);
+      g.bias = lw[GECCO_LW_MLP_B0]; g.act = 1; g.act_alpha = L.mlp_alpha;
+      g.out_bf16 = w.big; g.ldo16 = hid;
+      TRY(launch_gemm(g, s));
+      g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
+      g.bias = lw[GECCO_LW_MLP_B2];
+      g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
+      g.stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
+      TRY(launch_gemm(g, s));
+    }
+  }
+
+  // ---------------------------------------------------------------- output head + EDM preconditioning / sampler update
+  head.x = w.x; head.ldx = C;
+  head.clouds = clouds; head.rows_per_cloud = Np; head.valid_rows = points; head.c = C;
+  head.norm = d.head_norm; head.groups = d.head_groups; head.stats = head_stats; head.stat_gs = C / sg; head.eps = 1e-5f;
+  head.w_out = e->net[GECCO_NW_OUT_W]; head.b_out = e->net[GECCO_NW_OUT_B];
+  head.xin = xin;
+  head.sigma = w.sigma_eff; head.sigma_stride = 1; head.sigma_data = sigma_data;
+  return launch_head(head, s);
+}
+
+int check_common(const gecco_engine* e, int clouds, int points, const gecco_context& ctx, const void* ws, long long ws_bytes) {
+  GECCO_REQUIRE(e != nullptr, "null engine handle");
+  GECCO_REQUIRE(clouds > 0 && points > 0, "empty batch: clouds=%d points=%d", clouds, points);
+  GECCO_REQUIRE(ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be a 256-byte aligned device buffer");
+  const long long need = gecco_workspace_bytes(e, clouds, points);
+  GECCO_REQUIRE(ws_bytes >= need, "workspace too small: %lld bytes given, %lld needed", ws_bytes, need);
+  if (e->d.kind == 1) {
+    GECCO_REQUIRE(ctx.K != nullptr, "conditional model: camera matrices K are required");
+    for (int l = 0; l < e->d.n_levels; ++l)
+      GECCO_REQUIRE(ctx.level_ptr[l] != nullptr && ctx.level_h[l] > 0 && ctx.level_w[l] > 0,
+                    "conditional model: feature pyramid level %d is missing", l);
+  }
+  return GECCO_OK;
+}
+
+}  // namespace
+}  // namespace gecco
+
+using namespace gecco;
+
+extern "C" int gecco_create(const gecco_model_desc* desc, const float* const* net_weights, const float* const* layer_weights,
+                            void* stream, gecco_engine** out) {
+  GECCO_REQUIRE(desc && net_weights && layer_weights && out, "gecco_create: null argument");
+  const gecco_model_desc& d = *desc;
+  const int C = d.feature_dim, H = d.num_heads, I = d.num_inducers, hid = d.mlp_hidden;
+  GECCO_REQUIRE(d.kind == 0 || d.kind == 1, "gecco_create: unknown network kind %d", d.kind);
+  GECCO_REQUIRE(d.n_layers >= 1 && d.n_layers <= GECCO_MAX_LAYERS, "gecco_create: n_layers out of range");
+  GECCO_REQUIRE(C > 0 && C % 128 == 0 && C <= 1024, "gecco_create: feature_dim must be a multiple of 128 (<= 1024), got %d", C);
+  GECCO_REQUIRE(H > 0 && C % H == 0 && (C / H == 32 || C / H == 48 || C / H == 64),
+                "gecco_create: head dim must be 32, 48 or 64 (feature_dim %d, heads %d)", C, H);
+  GECCO_REQUIRE(I == 64, "gecco_create: only 64 inducers are supported (got %d)", I);
+  GECCO_REQUIRE(d.adagn_groups > 0 && C % d.adagn_groups == 0 && C / d.adagn_groups == 12,
+                "gecco_create: AdaGN groups must be 12 channels wide (feature_dim %d, groups %d)", C, d.adagn_groups);
+  GECCO_REQUIRE(hid > 0 && hid % 8 == 0, "gecco_create: mlp_hidden must be a multiple of 8");
+  GECCO_REQUIRE(d.head_norm >= 0 && d.head_norm <= 2, "gecco_create: bad head_norm");
+  GECCO_REQUIRE(d.head_norm != 2 || (d.head_groups > 0 && C % d.head_groups == 0 && (C / d.head_groups) % 12 == 0),
+                "gecco_create: head GroupNorm groups must be multiples of 12 channels");
+  int ctot = 0;
+  if (d.kind == 1) {
+    GECCO_REQUIRE(d.n_levels >= 1 && d.n_levels <= GECCO_MAX_LEVELS, "gecco_create: 1..%d pyramid levels", GECCO_MAX_LEVELS);
+    for (int l = 0; l < d.n_levels; ++l) {
+      GECCO_REQUIRE(d.level_c[l] > 0 && d.level_c[l] % 8 == 0, "gecco_create: level channel counts must be multiples of 8");
+      ctot += d.level_c[l];
+    }
+    GECCO_REQUIRE(d.img_groups > 0 && ctot % d.img_groups == 0, "gecco_create: image GroupNorm groups must divide %d", ctot);
+    GECCO_REQUIRE(net_weights[GECCO_NW_IMG_W] && net_weights[GECCO_NW_IMG_B], "gecco_create: image projection weights missing");
+  }
+  for (int i : {GECCO_NW_EMBED_W, GECCO_NW_EMBED_B, GECCO_NW_OUT_W, GECCO_NW_OUT_B})
+    GECCO_REQUIRE(net_weights[i] != nullptr, "gecco_create: network weight %d missing", i);
+  for (int i = 0; i < d.n_layers * GECCO_LW_COUNT; ++i)
+    GECCO_REQUIRE(layer_weights[i] != nullptr, "gecco_create: layer weight %d (layer %d, slot %d) missing", i,
+                  i / GECCO_LW_COUNT, i % GECCO_LW_COUNT);
+
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return fail_cuda(ce, "cudaGetDevice");
+  if (int rc = gecco_init(dev)) return rc;
+
+  gecco_engine* e = new (std::nothrow) gecco_engine();
+  GECCO_REQUIRE(e != nullptr, "gecco_create: out of host memory");
+  e->d = d;
+  e->device = dev;
+  for (int i = 0; i < GECCO_NW_COUNT; ++i) e->net[i] = net_weights[i];
+  e->lw.assign(layer_weights, layer_weights + (size_t)d.n_layers * GECCO_LW_COUNT);
+  e->layers.resize(d.n_layers);
+
+  const size_t per_layer_bf16 = (size_t)2 * C * C + (size_t)C * C + 2 * (size_t)hid * C + (size_t)C * C + (size_t)2 * C * C +
+                                (size_t)C * C + 2 * (size_t)hid * C + (size_t)H * I * (C / H);
+  size_t bytes = 0;
+  for (int l = 0; l < d.n_layers; ++l) bytes += align_up(per_layer_bf16 * 2 + 64 * 16) + align_up((size_t)C * 4);
+  bytes += align_up((size_t)C * 4) + 4096;
+  ce = cudaMalloc(&e->arena, bytes);
+  if (ce != cudaSuccess) {
+    delete e;
+    return fail_cuda(ce, "cudaMalloc(packed weights)");
+  }
+  e->arena_bytes = bytes;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Carver c{static_cast<uint8_t*>(e->arena)};
+  auto pack = [&](const float* src, size_t n, float scale) -> __nv_bfloat16* {
+    __nv_bfloat16* dst = c.take<__nv_bfloat16>(n);
+    pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, (long long)n, scale);
+    return dst;
+  };
+  // softmax scale and the exp -> exp2 change of base folded into the query side of both attentions
+  const float qscale = (float)(1.4426950408889634 / sqrt((double)(C / H)));
+  std::vector<float> alphas(2 * d.n_layers);
+  for (int l = 0; l < d.n_layers; ++l) {
+    const float* const* lw = layer_weights + (size_t)l * GECCO_LW_COUNT;
+    gecco_engine::Layer& L = e->layers[l];
+    L.pool_kv_w = pack(lw[GECCO_LW_POOL_KV_W], (size_t)2 * C * C, 1.f);
+    L.pool_out_w = pack(lw[GECCO_LW_POOL_OUT_W], (size_t)C * C, 1.f);
+    L.bmlp_w0 = pack(lw[GECCO_LW_BMLP_W0], (size_t)hid * C, 1.f);
+    L.bmlp_w2 = pack(lw[GECCO_LW_BMLP_W2], (size_t)C * hid, 1.f);
+    L.q_w = pack(lw[GECCO_LW_UNPOOL_IN_W], (size_t)C * C, qscale);                       // in_proj_weight[0:C]
+    L.kv_w = pack(lw[GECCO_LW_UNPOOL_IN_W] + (size_t)C * C, (size_t)2 * C * C, 1.f);      // in_proj_weight[C:3C]
+    L.out_w = pack(lw[GECCO_LW_UNPOOL_OUT_W], (size_t)C * C, 1.f);
+    L.mlp_w0 = pack(lw[GECCO_LW_MLP_W0], (size_t)hid * C, 1.f);
+    L.mlp_w2 = pack(lw[GECCO_LW_MLP_W2], (size_t)C * hid, 1.f);
+    L.q_ind = pack(lw[GECCO_LW_INDUCERS], (size_t)H * I * (C / H), qscale);
+    L.q_b = c.take<float>(C);
+    scale_add_f32_kernel<<<ceil_div(C, 256), 256, 0, s>>>(lw[GECCO_LW_UNPOOL_IN_B], nullptr, L.q_b, C, qscale);
+    cudaMemcpyAsync(&alphas[2 * l], lw[GECCO_LW_BMLP_ALPHA], sizeof(float), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&alphas[2 * l + 1], lw[GECCO_LW_MLP_ALPHA], sizeof(float), cudaMemcpyDeviceToHost, s);
+  }
+  e->img_bias = nullptr;
+  if (d.kind == 1) {
+    e->img_bias = c.take<float>(C);
+    scale_add_f32_kernel<<<ceil_div(C, 256), 256, 0, s>>>(net_weights[GECCO_NW_IMG_B], net_weights[GECCO_NW_EMBED_B],
+                                                          e->img_bias, C, 1.f);
+  }
+  ce = cudaStreamSynchronize(s);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (ce != cudaSuccess || c.off > bytes) {
+    cudaFree(e->arena);
+    delete e;
+    if (ce != cudaSuccess) return fail_cuda(ce, "gecco_create: weight packing");
+    set_error("gecco_create: internal arena overflow");
+    return GECCO_ERR_INVALID;
+  }
+  for (int l = 0; l < d.n_layers; ++l) {
+    e->layers[l].bmlp_alpha = alphas[2 * l];
+    e->layers[l].mlp_alpha = alphas[2 * l + 1];
+  }
+  *out = e;
+  return GECCO_OK;
+}
+
+extern "C" int gecco_destroy(gecco_engine* e) {
+  if (e == nullptr) return GECCO_OK;
+  cudaFree(e->arena);
+  delete e;
+  return GECCO_OK;
+}
+
+extern "C" int64_t gecco_workspace_bytes(const gecco_engine* e, int32_t clouds, int32_t points) {
+  if (e == nullptr || clouds <= 0 || points <= 0) return 0;
+  return (int64_t)carve(e, clouds, points, nullptr).bytes;
+}
+
+extern "C" int gecco_denoise(gecco_engine* e, const gecco_denoise_args* a, void* stream) {
+  GECCO_REQUIRE(a != nullptr, "gecco_denoise: null args");
+  TRY(check_common(e, a->clouds, a->points, a->ctx, a->workspace, a->workspace_bytes));
+  GECCO_REQUIRE(a->x != nullptr, "gecco_denoise: x is null");
+  GECCO_REQUIRE(a->mode >= 0 && a->mode <= 3, "gecco_denoise: bad mode %d", a->mode);
+  GECCO_REQUIRE(a->t_embed != nullptr || a->sigma != nullptr || a->sigma_imm > 0.f, "gecco_denoise: sigma missing");
+  GECCO_REQUIRE(a->t_embed == nullptr || a->mode == 0, "gecco_denoise: a network-level call (t_embed) only supports mode 0");
+  const Workspace w = carve(e, a->clouds, a->points, a->workspace);
+  gecco_head_args h = {};
+  h.mode = a->mode;
+  h.out_f32 = a->out;
+  h.x_hat = a->x_hat; h.x_next = a->x_next; h.d_cur = a->d_cur; h.xin_next = a->xin_next; h.noise_next = a->noise_next;
+  h.t_hat = a->t_hat; h.t_next = a->t_next; h.churn_next = a->churn_next;
+  return run_eval(e, w, a->x, a->sigma, a->sigma_stride, a->sigma_imm, a->t_embed, a->t_stride, a->clouds, a->points, a->ctx, a->cache_in,
+                  a->cache_out, h, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* stream) {
+  GECCO_REQUIRE(a != nullptr, "gecco_sample: null args");
+  TRY(check_common(e, a->clouds, a->points, a->ctx, a->workspace, a->workspace_bytes));
+  GECCO_REQUIRE(a->num_steps >= 1 && a->host_t_steps && a->host_gamma, "gecco_sample: schedule missing");
+  GECCO_REQUIRE(a->latents && a->noise && a->x_out, "gecco_sample: latents / noise / output missing");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Workspace w = carve(e, a->clouds, a->points, a->workspace);
+  const long long n3 = (long long)a->clouds * a->points * 3;
+  const double* t = a->host_t_steps;
+  auto churn = [&](int i) {  // sqrt(t_hat^2 - t_cur^2) * S_noise  (diffusion.py:323-325)
+    const double t_hat = t[i] + a->host_gamma[i] * t[i];
+    return sqrt(t_hat * t_hat - t[i] * t[i]) * a->s_noise;
+  };
+  // x_hat_0 = latents * t_0 + churn_0 * noise_0  (:308, :325)
+  TRY(launch_sampler_init(a->latents, a->noise, t[0], churn(0), n3, w.x_hat, w.xin_a, s));
+  for (int i = 0; i < a->num_steps; ++i) {
+    const double t_hat = t[i] + a->host_gamma[i] * t[i];
+    const double t_next = t[i + 1];
+    gecco_head_args h = {};
+    h.mode = 2;  // Euler (:335-336)
+    h.x_hat = w.x_hat; h.x_next = w.x_next; h.d_cur = w.d_cur; h.xin_next = w.xin_b;
+    h.t_hat = t_hat; h.t_next = t_next;
+    TRY(run_eval(e, w, w.xin_a, nullptr, 0, (float)t_hat, nullptr, 0, a->clouds, a->points, a->ctx, nullptr, nullptr, h, s));
+    if (i < a->num_steps - 1) {  // Heun (:339-347) + churn of step i+1
+      h.mode = 3;
+      h.xin_next = w.xin_a;
+      h.noise_next = a->noise + (size_t)(i + 1) * n3;
+      h.churn_next = churn(i + 1);
+      TRY(run_eval(e, w, w.xin_b, nullptr, 0, (float)t_next, nullptr, 0, a->clouds, a->points, a->ctx, nullptr, nullptr, h, s));
+    }
+  }
+  // the last step is Euler only: the result is x_next
+  copy_f64_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(w.x_next, a->x_out, n3);
+  GECCO_CHECK_LAUNCH("copy_f64_kernel");
+  return GECCO_OK;
+}

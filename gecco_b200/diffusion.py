@@ -1,0 +1,254 @@
+"""EDM-preconditioned diffusion model and its samplers, with gecco-torch's call surface
+(reference: gecco_torch/diffusion.py:22-470) on top of the CUDA engine.
+
+`Diffusion.forward` is one `gecco_denoise` call; `sample_stochastic` draws the noise exactly like the reference
+(one latent draw, then one [B,N,3] draw per step from the same generator) and runs the whole 2*num_steps-1
+evaluation loop in `gecco_sample`, where the preconditioning scales, churn, Euler and Heun updates are fused into
+the head kernel of each evaluation (float64 state, schedule computed on the host in float64).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from .engine import engine_for
+from .reparam import NoReparam, Reparam
+from .structs import Context3d, Example
+
+try:  # the reference derives from LightningModule purely for its training hooks (diffusion.py:168)
+    import lightning.pytorch as pl
+
+    _Base = pl.LightningModule
+except Exception:  # lightning is optional for sampling
+    _Base = nn.Module
+
+
+def ones(n: int):
+    return (1,) * n
+
+
+class EDMPrecond(nn.Module):
+    """Karras et al. preconditioning around a point network (diffusion.py:22-62):
+    D(x; sigma) = c_skip x + c_out F(c_in x, ln(sigma)/4).  Returns a Tensor, or (Tensor, cache) when do_cache."""
+
+    def __init__(self, model: nn.Module, sigma_data=1.0):
+        super().__init__()
+        self.model = model
+        self.sigma_data = sigma_data
+
+    def forward(self, x: Tensor, sigma: Tensor, raw_context: Any, post_context: Any, do_cache: bool = False,
+                cache: list[Tensor] | None = None):
+        K = raw_context.K if raw_context is not None else None
+        out, out_cache = engine_for(self.model, self.sigma_data).denoise(
+            x, sigma, post_context=post_context, K=K, cache=cache, do_cache=do_cache, mode=1)
+        out = out.to(x.dtype)
+        if not do_cache:
+            return out
+        return out, out_cache
+
+
+class LogUniformSchedule(nn.Module):
+    """Training noise levels, log-uniform in [min, max], stratified over the batch (diffusion.py:87-115)."""
+
+    def __init__(self, max: float, min: float = 0.002, low_discrepancy: bool = True):
+        super().__init__()
+        self.sigma_min = min
+        self.sigma_max = max
+        self.log_sigma_min = math.log(min)
+        self.log_sigma_max = math.log(max)
+        self.low_discrepancy = low_discrepancy
+
+    def extra_repr(self) -> str:
+        return f"sigma_min={self.sigma_min}, sigma_max={self.sigma_max}, low_discrepancy={self.low_discrepancy}"
+
+    def forward(self, data: Tensor) -> Tensor:
+        n = data.shape[0]
+        u = torch.rand(n, device=data.device)
+        if self.low_discrepancy:
+            u = (u + torch.arange(n, device=data.device)) / n
+        sigma = (u * (self.log_sigma_max - self.log_sigma_min) + self.log_sigma_min).exp()
+        return sigma.reshape(-1, *ones(data.ndim - 1))
+
+
+class EDMLoss(nn.Module):
+    """Weighted denoising loss (diffusion.py:118-143).  The CUDA engine is forward-only this round: the loss VALUE is
+    available (validation); gradients are not."""
+
+    def __init__(self, schedule: nn.Module, sigma_data: float = 1.0, loss_scale: float = 100.0):
+        super().__init__()
+        self.schedule = schedule
+        self.sigma_data = sigma_data
+        self.loss_scale = loss_scale
+
+    def extra_repr(self) -> str:
+        return f"sigma_data={self.sigma_data}, loss_scale={self.loss_scale}"
+
+    def forward(self, net: "Diffusion", examples: Tensor, context: Context3d) -> Tensor:
+        ex_diff = net.reparam.data_to_diffusion(examples, context)
+        sigma = self.schedule(ex_diff)
+        weight = (sigma**2 + self.sigma_data**2) / ((sigma * self.sigma_data) ** 2)
+        noisy = ex_diff + torch.randn_like(ex_diff) * sigma
+        D = net(noisy, sigma, context)
+        return (self.loss_scale * weight * (D - ex_diff) ** 2).mean()
+
+
+class Conditioner(nn.Module):
+    def forward(self, raw_context):
+        raise NotImplementedError()
+
+
+class IdleConditioner(Conditioner):
+    """Unconditional models have no context (diffusion.py:158-165)."""
+
+    def forward(self, raw_context: Context3d | None) -> None:
+        return None
+
+
+class Diffusion(_Base):
+    """backbone (EDMPrecond) + conditioner + loss + reparam, like the reference (diffusion.py:168-470)."""
+
+    def __init__(self, backbone: nn.Module, conditioner: Conditioner, loss: EDMLoss, reparam: Reparam = NoReparam(dim=3)):
+        super().__init__()
+        self.backbone = backbone
+        self.conditioner = conditioner
+        self.loss = loss
+        self.reparam = reparam
+        self.sampler_kwargs = dict(num_steps=64, sigma_min=0.002, sigma_max=self.sigma_max, rho=7, S_churn=0.5, S_min=0,
+                                   S_max=float("inf"), S_noise=1, with_pbar=False)
+
+    def extra_repr(self) -> str:
+        return str(self.sampler_kwargs)
+
+    @property
+    def sigma_max(self) -> float:
+        return self.loss.schedule.sigma_max
+
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.parameters(), lr=1e-4)
+
+    def training_step(self, batch: Example, batch_idx):
+        raise NotImplementedError("gecco_b200: the CUDA engine is forward-only; training is out of scope this round")
+
+    @torch.no_grad()
+    def validation_step(self, batch: Example, batch_idx):
+        x, ctx = batch
+        loss = self.loss(self, x, ctx)
+        if hasattr(self, "log"):
+            self.log("val_loss", loss)
+        return loss
+
+    def forward(self, data: Tensor, sigma: Tensor, raw_context: Any | None, post_context: Any | None = None,
+                do_cache: bool = False, cache: Any | None = None):
+        if post_context is None:
+            post_context = self.conditioner(raw_context)
+        return self.backbone(data, sigma, raw_context, post_context, do_cache, cache)
+
+    @property
+    def example_param(self) -> Tensor:
+        return next(self.parameters())
+
+    # ------------------------------------------------------------------ schedule
+    def t_steps(self, num_steps: int, sigma_max: float, sigma_min: float, rho: float) -> Tensor:
+        """float64 [num_steps + 1], last entry 0 (diffusion.py:253-269)."""
+        return self._t_steps_host(num_steps, sigma_max, sigma_min, rho).to(self.example_param.device)
+
+    @staticmethod
+    def _t_steps_host(num_steps: int, sigma_max: float, sigma_min: float, rho: float) -> Tensor:
+        idx = torch.arange(num_steps, dtype=torch.float64)
+        hi, lo = sigma_max ** (1 / rho), sigma_min ** (1 / rho)
+        t = (hi + idx / (num_steps - 1) * (lo - hi)) ** rho
+        return torch.cat([t, torch.zeros(1, dtype=torch.float64)])
+
+    @staticmethod
+    def _gammas(t_steps: Tensor, num_steps: int, S_churn, S_min, S_max) -> list[float]:
+        g = min(S_churn / num_steps, math.sqrt(2.0) - 1)
+        return [g if S_min <= t <= S_max else 0.0 for t in t_steps[:-1].tolist()]
+
+    @staticmethod
+    def _randn(shape, rng: torch.Generator, device, dtype) -> Tensor:
+        """Draws on the generator's own device (the reference requires generator and model on one device; a CPU
+        generator is additionally accepted here so that CPU-seeded noise can be reproduced bit for bit)."""
+        out = torch.randn(tuple(shape), device=rng.device, generator=rng, dtype=dtype)
+        return out if out.device == device else out.to(device, non_blocking=True)
+
+    # ------------------------------------------------------------------ samplers
+    @torch.no_grad()
+    def sample_stochastic(self, shape: Sequence[int], context: Context3d | None, rng: torch.Generator = None, **kwargs) -> Tensor:
+        """Stochastic EDM sampler (Karras Alg. 2 with Heun correction), diffusion.py:271-352.  Returns float64 data-space points."""
+        kw = {**self.sampler_kwargs, **kwargs}
+        num_steps = kw["num_steps"]
+        device, dtype = self.example_param.device, self.example_param.dtype
+        if rng is None:
+            rng = torch.Generator(device).manual_seed(42)
+        latents = self._randn(shape, rng, device, dtype)
+        post_context = self.conditioner(context)
+        ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])
+        gammas = self._gammas(ts, num_steps, kw["S_churn"], kw["S_min"], kw["S_max"])
+        # one draw per step, even where gamma is 0 (diffusion.py:324)
+        noise = torch.stack([self._randn(latents.shape, rng, device, dtype) for _ in range(num_steps)])
+        net, sigma_data = self._network()
+        x = engine_for(net, sigma_data).sample(latents, noise, ts.tolist(), gammas, kw["S_noise"], post_context=post_context,
+                                               K=None if context is None else context.K)
+        return self.reparam.diffusion_to_data(x, context)
+
+    def _network(self):
+        bb = self.backbone
+        if not isinstance(bb, EDMPrecond):
+            raise TypeError("gecco_b200: Diffusion.backbone must be an EDMPrecond")
+        return bb.model, bb.sigma_data
+
+    @torch.no_grad()
+    def upsample(self, data: Tensor, new_latents: Tensor | None = None, n_new: int | None = None,
+                 context: Context3d | None = None, seed: int | None = 42, num_substeps=5, **kwargs):
+        """Conditional upsampling with cached inducer states (diffusion.py:354-470).  The conditioner runs once (the
+        reference re-runs it on every call, with identical results in eval mode)."""
+        rng = kwargs.pop("rng", None)  # extension: an explicit (e.g. CPU) generator instead of `seed`
+        kw = {**self.sampler_kwargs, **kwargs}
+        num_steps, S_churn, S_min, S_max, S_noise = kw["num_steps"], kw["S_churn"], kw["S_min"], kw["S_max"], kw["S_noise"]
+        device, dtype = self.example_param.device, self.example_param.dtype
+        if rng is None:
+            rng = torch.Generator(device)
+            if seed is not None:
+                rng.manual_seed(seed)
+        randn = lambda shape: self._randn(shape, rng, device, dtype)
+        if (new_latents is None) == (n_new is None):
+            raise ValueError("Either new_latents or n_new must be specified, but not both.")
+        if new_latents is None:
+            new_latents = randn((data.shape[0], n_new, data.shape[2]))
+        assert isinstance(new_latents, Tensor)
+        data = self.reparam.data_to_diffusion(data, context)
+        post_context = self.conditioner(context)
+        ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])
+        gammas = self._gammas(ts, num_steps, S_churn, S_min, S_max)
+        net, sigma_data = self._network()
+        eng = engine_for(net, sigma_data)
+        K = None if context is None else context.K
+        B = data.shape[0]
+        tl = ts.tolist()
+        x_next = new_latents.to(torch.float64) * tl[0]
+        for i in range(num_steps):
+            t_cur, t_next = tl[i], tl[i + 1]
+            data_ctx = data + randn(data.shape) * t_cur
+            sig = torch.full((B,), t_cur, device=device, dtype=torch.float64).to(dtype)
+            _, cache = eng.denoise(data_ctx.to(dtype), sig, post_context=post_context, K=K, do_cache=True)
+            for u in range(num_substeps):
+                x_cur = x_next
+                t_hat = t_cur + gammas[i] * t_cur
+                churn = torch.tensor(math.sqrt(t_hat**2 - t_cur**2) * S_noise, dtype=dtype, device=device)
+                x_hat = x_cur + churn * randn(x_cur.shape)
+                sig = torch.full((B,), t_hat, device=device, dtype=torch.float64).to(dtype)
+                den, _ = eng.denoise(x_hat.to(dtype), sig, post_context=post_context, K=K, cache=cache)
+                d_cur = (x_hat - den.to(torch.float64)) / t_hat
+                x_next = x_hat + (t_next - t_hat) * d_cur
+                if i < num_steps - 1:
+                    sig = torch.full((B,), t_next, device=device, dtype=torch.float64).to(dtype)
+                    den, _ = eng.denoise(x_next.to(dtype), sig, post_context=post_context, K=K, cache=cache)
+                    d_prime = (x_next - den.to(torch.float64)) / t_next
+                    x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
+                if u < num_substeps - 1 and i < num_steps - 1:
+                    redo = torch.tensor(math.sqrt(t_cur**2 - t_next**2), dtype=dtype, device=device)
+                    x_next = x_next + redo * randn(x_next.shape)
+        return self.reparam.diffusion_to_data(x_next, context)

@@ -1,0 +1,296 @@
+"""Host side of the denoiser engine: walks a LinearLift / RayNetwork module tree, hands its fp32 parameters
+(reference state_dict schema) to `gecco_create`, and exposes one denoiser evaluation
+(`gecco_denoise`) and the whole stochastic sampler loop (`gecco_sample`).
+
+Torch is used for memory (parameters, workspace, outputs) and the current stream only.  There is no
+fallback: a missing library, a CPU tensor or a non-sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _abi, ops
+from .structs import FeaturePyramidContext
+
+_NORM_LEAVES = ("scale.weight", "scale.bias", "bias.weight", "bias.bias")
+
+
+def _get(mod, path: str):
+    for part in path.split("."):
+        mod = mod[int(part)] if part.isdigit() else getattr(mod, part)
+    return mod
+
+
+def _layer_tensors(layer) -> list:
+    """fp32 tensors of one BroadcastingLayer in gecco_layer_weight order (include/gecco_b200.h)."""
+    t = []
+    t += [_get(layer, "broadcast_norm." + n) for n in _NORM_LEAVES]
+    t += [layer.broadcast.pool.inducers, layer.broadcast.pool.kv_proj.weight, layer.broadcast.pool.out_proj.weight]
+    t += [_get(layer, "broadcast.norm_1." + n) for n in _NORM_LEAVES]
+    m = layer.broadcast.mlp
+    t += [m[0].weight, m[0].bias, m[1].alpha, m[2].weight, m[2].bias]
+    t += [_get(layer, "broadcast.norm_2." + n) for n in _NORM_LEAVES]
+    u = layer.broadcast.unpool
+    t += [u.in_proj_weight, u.in_proj_bias, u.out_proj.weight, u.out_proj.bias]
+    t += [_get(layer, "mlp_norm." + n) for n in _NORM_LEAVES]
+    m = layer.mlp
+    t += [m[0].weight, m[0].bias, m[1].alpha, m[2].weight, m[2].bias]
+    assert len(t) == _abi.LW_COUNT
+    return t
+
+
+class Engine:
+    """Native denoiser for one network module (LinearLift or RayNetwork) and one sigma_data."""
+
+    def __init__(self, network: torch.nn.Module, sigma_data: float = 1.0):
+        self._network_ref = weakref.ref(network)
+        self.sigma_data = float(sigma_data)
+        self._handle: Optional[C.c_void_p] = None
+        self._key = None
+        self._keepalive = None
+        self._ws: Optional[Tensor] = None
+        self._packed_key = None
+        self._packed = None
+        self._lib = None
+
+    # ------------------------------------------------------------------ handle management
+    def _describe(self):
+        from .models.activation import GaussianActivation
+        from .models.linear_lift import LinearLift
+        from .models.ray import RayNetwork
+
+        net = self._network_ref()
+        if net is None:
+            raise _abi.GeccoError("gecco_b200: the network module of this engine no longer exists")
+        d = _abi.ModelDesc()
+        if isinstance(net, LinearLift):
+            d.kind = 0
+            st = net.inner
+            embed = net.lift
+            if isinstance(net.lower, torch.nn.Sequential):
+                out, d.head_norm = net.lower[1], 1
+            else:
+                out, d.head_norm = net.lower, 0
+            img = None
+            d.head_groups, d.img_groups, d.n_levels, d.reparam = 1, 1, 0, 0
+        elif isinstance(net, RayNetwork):
+            d.kind = 1
+            st = net.backbone
+            embed, img, out = net.xyz_embed, net.img_feature_proj[1], net.output_proj[1]
+            d.head_norm, d.head_groups, d.img_groups = 2, net.output_proj[0].num_groups, net.img_feature_proj[0].num_groups
+            dims = list(net.context_dims)
+            if len(dims) > _abi.MAX_LEVELS:
+                raise ValueError(f"gecco_b200: at most {_abi.MAX_LEVELS} feature pyramid levels are supported")
+            d.n_levels = len(dims)
+            for i, c in enumerate(dims):
+                d.level_c[i] = int(c)
+            rp = net.reparam
+            d.reparam = rp._kind
+            mean, sigma, logit_scale = rp._host_stats()
+            for j in range(3):
+                d.mean[j] = 0.0 if mean is None else mean[j]
+                d.sigma[j] = 1.0 if sigma is None else sigma[j]
+            d.logit_scale = logit_scale
+        else:
+            raise TypeError(f"gecco_b200: unsupported network module {type(net).__name__} (LinearLift or RayNetwork expected)")
+        layers = list(st.layers)
+        l0 = layers[0]
+        d.n_layers = len(layers)
+        d.feature_dim = st.feature_dim
+        d.num_heads = l0.broadcast.pool.num_heads
+        d.num_inducers = l0.broadcast.pool.inducers.shape[2]
+        d.mlp_hidden = l0.mlp[0].out_features
+        d.adagn_groups = l0.broadcast_norm.gn.num_groups
+        d.sigma_data = self.sigma_data
+        for layer in layers:
+            for m in (layer.mlp, layer.broadcast.mlp):
+                if len(m) != 3 or not isinstance(m[1], GaussianActivation) or not m[1].normalized:
+                    raise ValueError("gecco_b200: the CUDA path supports depth-1 MLPs with the normalised GaussianActivation only")
+            if layer.broadcast_norm.scale.weight.shape[1] != 1:
+                raise ValueError("gecco_b200: t_embed_dim must be 1")
+        net_t = [embed.weight, embed.bias, None if img is None else img.weight, None if img is None else img.bias,
+                 out.weight, out.bias]
+        layer_t = [t for layer in layers for t in _layer_tensors(layer)]
+        return d, net_t, layer_t
+
+    def _ensure(self, device: torch.device):
+        desc, net_t, layer_t = self._describe()
+        tensors = [t for t in net_t if t is not None] + layer_t
+        for t in tensors:
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise _abi.GeccoError("gecco_b200: model parameters must be float32 CUDA tensors (there is no CPU path); "
+                                      "move the model with .to('cuda')")
+            if t.device != device:
+                raise _abi.GeccoError("gecco_b200: inputs and parameters are on different devices")
+        key = (tuple((t.data_ptr(), t._version) for t in tensors), bytes(desc))
+        if self._handle is not None and key == self._key:
+            return
+        self.close()
+        lib = _abi.init(device.index if device.index is not None else torch.cuda.current_device())
+        keep = [t.detach().contiguous() for t in tensors]
+        it = iter(keep)
+        net_ptrs = (C.c_void_p * _abi.NW_COUNT)(*[None if t is None else next(it).data_ptr() for t in net_t])
+        layer_ptrs = (C.c_void_p * len(layer_t))(*[next(it).data_ptr() for _ in layer_t])
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            _abi.check(lib.gecco_create(C.byref(desc), net_ptrs, layer_ptrs, stream, C.byref(handle)))
+        self._handle, self._key, self._keepalive, self._lib = handle, key, keep, lib
+        self._desc = desc
+
+    def close(self):
+        if self._handle is not None and self._lib is not None:
+            self._lib.gecco_destroy(self._handle)
+        self._handle = None
+        self._key = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ buffers
+    def _workspace(self, clouds: int, points: int, device) -> Tensor:
+        need = int(self._lib.gecco_workspace_bytes(self._handle, clouds, points))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = None
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _context(self, post_context, K: Optional[Tensor], clouds: int) -> tuple[_abi.Context, list]:
+        ctx = _abi.Context()
+        keep = []
+        if self._desc.kind == 0:
+            return ctx, keep
+        if post_context is None or K is None:
+            raise ValueError("gecco_b200: a conditional model needs the feature pyramid (post_context) and camera matrices")
+        feats: Sequence[Tensor] = post_context.features if isinstance(post_context, FeaturePyramidContext) else post_context
+        if len(feats) != self._desc.n_levels:
+            raise ValueError(f"gecco_b200: expected {self._desc.n_levels} feature maps, got {len(feats)}")
+        pkey = tuple((f.data_ptr(), f._version, tuple(f.shape)) for f in feats)
+        if self._packed_key != pkey:
+            packed = []
+            for i, f in enumerate(feats):
+                if f.shape[0] != clouds or f.shape[1] != self._desc.level_c[i]:
+                    raise ValueError(f"gecco_b200: feature map {i} has shape {tuple(f.shape)}, expected [{clouds}, {self._desc.level_c[i]}, H, W]")
+                packed.append(ops.pack_features(f))
+            self._packed_key, self._packed = pkey, packed
+        for i, p in enumerate(self._packed):
+            ctx.level_ptr[i] = p.data_ptr()
+            ctx.level_h[i], ctx.level_w[i] = p.shape[1], p.shape[2]
+        Kc = K.detach().to(torch.float32).contiguous()
+        if Kc.shape != (clouds, 3, 3):
+            raise ValueError(f"gecco_b200: K must be [{clouds}, 3, 3], got {tuple(Kc.shape)}")
+        ctx.K = Kc.data_ptr()
+        keep.append(Kc)
+        return ctx, keep
+
+    # ------------------------------------------------------------------ calls
+    @torch.no_grad()
+    def denoise(self, x: Tensor, sigma: Optional[Tensor] = None, *, t_embed: Optional[Tensor] = None, post_context=None,
+                K: Optional[Tensor] = None, cache: Optional[Sequence[Tensor]] = None, do_cache: bool = False,
+                mode: int = 1):
+        """One evaluation.  mode 1: EDM-preconditioned denoised output D(x; sigma); mode 0: raw network output
+        (with `t_embed`, x is the already scaled geometry: LinearLift.forward / RayNetwork.forward)."""
+        if not x.is_cuda:
+            raise _abi.GeccoError("gecco_b200 needs CUDA tensors (there is no CPU path)")
+        if x.ndim != 3 or x.shape[-1] != 3:
+            raise ValueError(f"gecco_b200: geometry must be [batch, points, 3], got {tuple(x.shape)}")
+        self._ensure(x.device)
+        B, N = x.shape[0], x.shape[1]
+        xf = x.detach().to(torch.float32).contiguous()
+        a = _abi.DenoiseArgs()
+        a.x = xf.data_ptr()
+        a.clouds, a.points = B, N
+        keep = [xf]
+        if t_embed is not None:
+            te = t_embed.detach().to(torch.float32).reshape(-1).contiguous()
+            if te.numel() != B:
+                raise ValueError("gecco_b200: t_embed must hold one value per cloud")
+            a.t_embed, a.t_stride = te.data_ptr(), 1
+            keep.append(te)
+            mode = 0
+        else:
+            sg = sigma.detach().to(torch.float32).reshape(-1).contiguous()
+            if sg.numel() not in (1, B):
+                raise ValueError("gecco_b200: sigma must hold one value per cloud")
+            a.sigma, a.sigma_stride = sg.data_ptr(), (0 if sg.numel() == 1 else 1)
+            keep.append(sg)
+        ctx, k2 = self._context(post_context, K, B)
+        a.ctx = ctx
+        keep += k2
+        L, I, Cf = self._desc.n_layers, self._desc.num_inducers, self._desc.feature_dim
+        if cache is not None:
+            if len(cache) != L:
+                raise ValueError(f"gecco_b200: cache must hold {L} inducer states")
+            cin = torch.stack([c.detach().to(torch.float32) for c in cache]).contiguous()
+            if cin.shape != (L, B, I, Cf):
+                raise ValueError(f"gecco_b200: cached inducer states must be [{B}, {I}, {Cf}]")
+            a.cache_in = cin.data_ptr()
+            keep.append(cin)
+        cout = None
+        if do_cache:
+            if cache is not None:
+                cout = cin  # the reference hands the given states back (set_transformer.py:114-115)
+            else:
+                cout = torch.empty((L, B, I, Cf), device=x.device, dtype=torch.float32)
+                a.cache_out = cout.data_ptr()
+        out = torch.empty((B, N, 3), device=x.device, dtype=torch.float32)
+        a.mode, a.out = mode, out.data_ptr()
+        ws = self._workspace(B, N, x.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            _abi.check(self._lib.gecco_denoise(self._handle, C.byref(a), stream))
+        del keep
+        return out, (None if cout is None else [cout[l] for l in range(L)])
+
+    @torch.no_grad()
+    def sample(self, latents: Tensor, noise: Tensor, t_steps: Sequence[float], gammas: Sequence[float], s_noise: float,
+               post_context=None, K: Optional[Tensor] = None) -> Tensor:
+        """The stochastic sampler loop of Diffusion.sample_stochastic on pre-drawn noise.
+        latents [B,N,3] fp32, noise [num_steps,B,N,3] fp32; returns the float64 diffusion-space result."""
+        if not latents.is_cuda:
+            raise _abi.GeccoError("gecco_b200 needs CUDA tensors (there is no CPU path)")
+        self._ensure(latents.device)
+        B, N = latents.shape[0], latents.shape[1]
+        steps = len(gammas)
+        assert len(t_steps) == steps + 1 and noise.shape == (steps, B, N, 3)
+        lat = latents.detach().to(torch.float32).contiguous()
+        nz = noise.detach().to(torch.float32).contiguous()
+        a = _abi.SampleArgs()
+        a.clouds, a.points, a.num_steps = B, N, steps
+        ts = (C.c_double * (steps + 1))(*[float(t) for t in t_steps])
+        gs = (C.c_double * steps)(*[float(g) for g in gammas])
+        a.host_t_steps, a.host_gamma, a.s_noise = ts, gs, float(s_noise)
+        a.latents, a.noise = lat.data_ptr(), nz.data_ptr()
+        ctx, keep = self._context(post_context, K, B)
+        a.ctx = ctx
+        out = torch.empty((B, N, 3), device=latents.device, dtype=torch.float64)
+        a.x_out = out.data_ptr()
+        ws = self._workspace(B, N, latents.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(latents.device):
+            stream = C.c_void_p(torch.cuda.current_stream(latents.device).cuda_stream)
+            _abi.check(self._lib.gecco_sample(self._handle, C.byref(a), stream))
+        del keep
+        return out
+
+
+_ENGINES: "weakref.WeakKeyDictionary[torch.nn.Module, dict]" = weakref.WeakKeyDictionary()
+
+
+def engine_for(network: torch.nn.Module, sigma_data: float = 1.0) -> Engine:
+    """The (cached) engine of a network module.  Kept outside the module so that state_dict(), deepcopy and
+    pickling of the model are unaffected."""
+    cache = _ENGINES.setdefault(network, {})
+    key = float(sigma_data)
+    if key not in cache:
+        cache[key] = Engine(network, sigma_data)
+    return cache[key]

@@ -217,6 +217,113 @@ typedef struct gecco_unpool_args {
 } gecco_unpool_args;
 int gecco_unpool_attention(const gecco_unpool_args* args, void* stream);
 
+/* ========================================================================
+ * Denoiser engine: one handle per (model, device).  This is the entry a maintainer binds in place of
+ * Diffusion.forward / EDMPrecond.forward (diffusion.py:233-247, 37-62) and of the body of
+ * Diffusion.sample_stochastic / Diffusion.upsample (diffusion.py:271-352, 354-470).
+ * ======================================================================== */
+#define GECCO_MAX_LAYERS 32
+
+typedef struct gecco_model_desc {
+  int32_t kind;          /* 0: LinearLift (models/linear_lift.py), 1: RayNetwork (models/ray.py) */
+  int32_t n_layers, feature_dim, num_heads, num_inducers, mlp_hidden;
+  int32_t adagn_groups;  /* 32 (models/normalization.py:19) */
+  int32_t head_norm;     /* 0 none, 1 LayerNorm (linear_lift.py:26-29), 2 GroupNorm over points (ray.py:56-59) */
+  int32_t head_groups;   /* 16 */
+  int32_t img_groups;    /* 16 (ray.py:53) */
+  int32_t n_levels; int32_t level_c[GECCO_MAX_LEVELS];
+  int32_t reparam;       /* reparam of the lookup: 0 none, 1 gaussian, 2 uvl (ray.py:71) */
+  float mean[3], sigma[3], logit_scale;
+  float sigma_data;      /* EDMPrecond.sigma_data (diffusion.py:31) */
+} gecco_model_desc;
+
+/* fp32 device pointers in the reference state_dict schema. */
+enum gecco_net_weight {
+  GECCO_NW_EMBED_W = 0,  /* lift.weight | xyz_embed.weight           [C,3] */
+  GECCO_NW_EMBED_B,      /* lift.bias | xyz_embed.bias               [C]   */
+  GECCO_NW_IMG_W,        /* img_feature_proj.1.weight (cond)         [C, sum level_c] */
+  GECCO_NW_IMG_B,        /* img_feature_proj.1.bias (cond)           [C]   */
+  GECCO_NW_OUT_W,        /* lower.1.weight | output_proj.1.weight    [3,C] */
+  GECCO_NW_OUT_B,        /* lower.1.bias | output_proj.1.bias        [3]   */
+  GECCO_NW_COUNT
+};
+enum gecco_layer_weight {      /* `layers.{l}.` + ...  (models/set_transformer.py) */
+  GECCO_LW_BN = 0,             /* broadcast_norm.{scale.weight, scale.bias, bias.weight, bias.bias}: 4 entries */
+  GECCO_LW_INDUCERS = 4,       /* broadcast.pool.inducers          [1,H,I,d] */
+  GECCO_LW_POOL_KV_W,          /* broadcast.pool.kv_proj.weight    [2C,C] */
+  GECCO_LW_POOL_OUT_W,         /* broadcast.pool.out_proj.weight   [C,C]  */
+  GECCO_LW_N1 = 7,             /* broadcast.norm_1.*: 4 entries */
+  GECCO_LW_BMLP_W0 = 11,       /* broadcast.mlp.0.weight [hid,C], .0.bias, .1.alpha (scalar), .2.weight [C,hid], .2.bias */
+  GECCO_LW_BMLP_B0, GECCO_LW_BMLP_ALPHA, GECCO_LW_BMLP_W2, GECCO_LW_BMLP_B2,
+  GECCO_LW_N2 = 16,            /* broadcast.norm_2.*: 4 entries */
+  GECCO_LW_UNPOOL_IN_W = 20,   /* broadcast.unpool.in_proj_weight [3C,C], in_proj_bias [3C], out_proj.weight [C,C], out_proj.bias [C] */
+  GECCO_LW_UNPOOL_IN_B, GECCO_LW_UNPOOL_OUT_W, GECCO_LW_UNPOOL_OUT_B,
+  GECCO_LW_MN = 24,            /* mlp_norm.*: 4 entries */
+  GECCO_LW_MLP_W0 = 28,        /* mlp.0.weight, .0.bias, .1.alpha, .2.weight, .2.bias */
+  GECCO_LW_MLP_B0, GECCO_LW_MLP_ALPHA, GECCO_LW_MLP_W2, GECCO_LW_MLP_B2,
+  GECCO_LW_COUNT = 33
+};
+
+typedef struct gecco_engine gecco_engine;
+
+/* Packs the fp32 weights into the kernel layouts (bf16 operands, folded softmax scale).  The fp32 arrays
+ * that are used in place (biases, AdaGN linears, embed / head weights) must stay alive and unchanged
+ * until gecco_destroy; re-create the handle after a weight update.  Synchronises `stream` once. */
+int gecco_create(const gecco_model_desc* desc, const float* const* net_weights /* [GECCO_NW_COUNT] */,
+                 const float* const* layer_weights /* [n_layers * GECCO_LW_COUNT] */, void* stream,
+                 gecco_engine** out);
+int gecco_destroy(gecco_engine* e);
+/* Scratch needed by gecco_denoise / gecco_sample for `clouds` clouds of `points` points. */
+int64_t gecco_workspace_bytes(const gecco_engine* e, int32_t clouds, int32_t points);
+
+typedef struct gecco_context {          /* conditional models only */
+  const void* level_ptr[GECCO_MAX_LEVELS];        /* bf16 NHWC pyramid levels (gecco_pack_features) */
+  int32_t level_h[GECCO_MAX_LEVELS], level_w[GECCO_MAX_LEVELS];
+  const float* K;                                  /* [clouds,3,3] */
+} gecco_context;
+
+/* One denoiser evaluation (Diffusion.forward -> EDMPrecond.forward -> network):
+ *   mode 0: out = F(c_in x, ln(sigma)/4)             raw network output
+ *   mode 1: out = c_skip x + c_out F                 (diffusion.py:57)
+ *   mode 2 / 3: Euler / Heun(+churn) update of the float64 sampler state, see gecco_head_args.
+ * cache_in  != NULL: inducer states h [n_layers][clouds][inducers][C] fp32 are used instead of pooling
+ *                    (set_transformer.py:106-110, the upsampling fast path);
+ * cache_out != NULL: the inducer states of this evaluation are written there (do_cache). */
+typedef struct gecco_denoise_args {
+  const float* x;                      /* [clouds, points, 3] */
+  const float* sigma; int32_t sigma_stride; float sigma_imm; /* sigma[cloud*stride], or sigma_imm when NULL */
+  /* network-level call (LinearLift.forward / RayNetwork.forward, mode 0 only): when t_embed != NULL, x is the
+   * already scaled geometry and t_embed[cloud*t_stride] the noise embedding; sigma is ignored. */
+  const float* t_embed; int32_t t_stride;
+  int32_t clouds, points;
+  gecco_context ctx;
+  const float* cache_in; float* cache_out;
+  int32_t mode;
+  float* out;
+  double* x_hat; double* x_next; double* d_cur; float* xin_next; const float* noise_next;
+  double t_hat, t_next, churn_next;
+  void* workspace; int64_t workspace_bytes;
+} gecco_denoise_args;
+int gecco_denoise(gecco_engine* e, const gecco_denoise_args* args, void* stream);
+
+/* The whole stochastic sampler loop (diffusion.py:305-347) on pre-drawn noise: 2*num_steps-1 evaluations with
+ * the preconditioning, churn, Euler and Heun arithmetic fused into the head kernel of each evaluation.
+ * host_t_steps: float64 [num_steps+1] (Diffusion.t_steps, last = 0); host_gamma: float64 [num_steps]
+ * (diffusion.py:318-322).  noise: [num_steps][clouds][points][3] in the reference draw order.
+ * x_out: float64 [clouds, points, 3], the diffusion-space result (reparam.diffusion_to_data is applied by the caller). */
+typedef struct gecco_sample_args {
+  int32_t clouds, points, num_steps;
+  const double* host_t_steps; const double* host_gamma; double s_noise;
+  const float* latents; const float* noise;
+  gecco_context ctx;
+  double* x_out;
+  void* workspace; int64_t workspace_bytes;
+} gecco_sample_args;
+int gecco_sample(gecco_engine* e, const gecco_sample_args* args, void* stream);
+
+/* Number of kernel launches the library has issued on this thread since the last call (bench bookkeeping). */
+int64_t gecco_launch_count(int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

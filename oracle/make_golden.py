@@ -74,6 +74,17 @@ def build_reference(kind: str, reparam: str, mean, sigma, sigma_max: float, feat
     return model.eval()
 
 
+def rel_rms(a: torch.Tensor, b: torch.Tensor) -> float:
+    return ((a.double() - b.double()).pow(2).mean().sqrt() / b.double().pow(2).mean().sqrt()).item()
+
+
+def bf16_drift(fn) -> torch.Tensor:
+    """Runs `fn` under the reference's own mixed precision (torch CPU autocast, bfloat16): the drift of the UNMODIFIED
+    reference at the precision the CUDA path computes in.  Stored next to the fp32 goldens to calibrate tolerances."""
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        return fn()
+
+
 def sub(t: torch.Tensor) -> torch.Tensor:
     """strided sub-sample of an inducer state [B, 64, C] (keeps fixtures small)"""
     return t[:, ::8, ::8].contiguous()
@@ -101,7 +112,10 @@ def main():
         D_cached = model(x2, sig, None, cache=hs)
         samp = model.sample_stochastic((2, 256, 3), None, rng=synth.gen(42), num_steps=6)
         ts = model.t_steps(64, 165.0, 0.002, 7)
-    torch.save(dict(recipe={**recipe_common, **cfg, "x_seed": 11, "x_scale": 3.0, "B": B, "N": N, "noise_sigma": sig,
+    drift = dict(D=rel_rms(bf16_drift(lambda: model(x, sig, None)).float(), D),
+                 sample=rel_rms(bf16_drift(lambda: model.sample_stochastic((2, 256, 3), None, rng=synth.gen(42), num_steps=6)), samp))
+    print("uncond bf16-autocast drift of the reference", drift)
+    torch.save(dict(drift=drift, recipe={**recipe_common, **cfg, "x_seed": 11, "x_scale": 3.0, "B": B, "N": N, "noise_sigma": sig,
                             "x2_seed": 12, "N2": 200, "sample_shape": (2, 256, 3), "sample_seed": 42, "sample_steps": 6},
                     D=D, hs_sub=[sub(h) for h in hs], D_cached=D_cached, sample=samp, t_steps=ts),
                OUT / "uncond.pt")
@@ -122,7 +136,10 @@ def main():
         c_in = 1 / (1 + sig**2).sqrt()
         look = model.backbone.model.extract_image_features(x * c_in[:, None, None], feats, ctx)
         samp = model.sample_stochastic((2, 200, 3), ctx, rng=synth.gen(43), num_steps=5)
-    torch.save(dict(recipe={**recipe_common, **cfg, "K": synth.K_SHAPENET, "feat_sizes": (34, 17, 8), "feat_seed": 21,
+    drift = dict(D=rel_rms(bf16_drift(lambda: model(x, sig, ctx)).float(), D),
+                 sample=rel_rms(bf16_drift(lambda: model.sample_stochastic((2, 200, 3), ctx, rng=synth.gen(43), num_steps=5)), samp))
+    print("cond_gaussian bf16-autocast drift of the reference", drift)
+    torch.save(dict(drift=drift, recipe={**recipe_common, **cfg, "K": synth.K_SHAPENET, "feat_sizes": (34, 17, 8), "feat_seed": 21,
                             "x_seed": 22, "x_scale": 2.0, "B": B, "N": N, "noise_sigma": sig,
                             "sample_shape": (2, 200, 3), "sample_seed": 43, "sample_steps": 5},
                     D=D, lookup_sub=look[:, ::3].contiguous(), sample=samp),
@@ -153,7 +170,14 @@ def main():
         # upsample (diffusion.py:354-470): seed cloud in data space, in frustum
         seed_cloud = model.reparam.diffusion_to_data(torch.randn(B, 128, 3, generator=synth.gen(35)), ctx)
         ups = model.upsample(seed_cloud, n_new=384, context=ctx, seed=7, num_substeps=2, num_steps=3)
-    torch.save(dict(recipe={**recipe_common, **cfg, "K": synth.K_TASKONOMY, "feat_sizes": (64, 32, 16), "feat_seed": 31,
+    to_diff = lambda d: model.reparam.data_to_diffusion(d, Context3d(image=ctx.image, K=K.double()))
+    drift = dict(D=rel_rms(bf16_drift(lambda: model(x, sig, ctx)).float(), D),
+                 sample=rel_rms(to_diff(bf16_drift(lambda: model.sample_stochastic((2, 192, 3), ctx, rng=synth.gen(44), num_steps=5))),
+                                to_diff(samp)),
+                 upsample=rel_rms(to_diff(bf16_drift(lambda: model.upsample(seed_cloud, n_new=384, context=ctx, seed=7,
+                                                                              num_substeps=2, num_steps=3))), to_diff(ups)))
+    print("cond_uvl bf16-autocast drift of the reference (samples in diffusion space)", drift)
+    torch.save(dict(drift=drift, recipe={**recipe_common, **cfg, "K": synth.K_TASKONOMY, "feat_sizes": (64, 32, 16), "feat_seed": 31,
                             "x_seed": 32, "x_scale": 1.5, "B": B, "N": N, "noise_sigma": sig, "x2_seed": 33, "N2": 500,
                             "sample_shape": (2, 192, 3), "sample_seed": 44, "sample_steps": 5,
                             "rt_seed": 34, "ups_seed_cloud_seed": 35, "ups_n_seed": 128, "ups_n_new": 384,
