@@ -175,6 +175,11 @@ class SampleArgs(C.Structure):
     ]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 

@@ -7,7 +7,51 @@
 
 #include <math.h>
 #include <new>
+#include <string.h>
 #include <vector>
+
+// ---------------------------------------------------------------------------------------------
+// Per-kernel-class device timing (gecco_profile_start / gecco_profile_stop): when enabled, every launch of the
+// engine is bracketed by CUDA events on the launching stream and attributed to a class together with its
+// algorithmic FLOPs and bytes.  Off by default (no events, no overhead).
+namespace gecco {
+namespace {
+enum KClass {
+  K_PREP = 0, K_LIFT, K_LOOKUP, K_FOLD_GN, K_GEMM_IMG, K_ADAGN, K_GEMM_POOL_KV, K_POOL_ATTN, K_INDUCER_CHAIN,
+  K_GEMM_UNPOOL_Q, K_UNPOOL_ATTN, K_GEMM_UNPOOL_OUT, K_GEMM_MLP0, K_GEMM_MLP2, K_HEAD, K_MISC, K_COUNT
+};
+const char* const kClassNames[K_COUNT] = {
+    "prep", "lift", "lookup", "fold_group_norm", "gemm_img_proj", "adagn_apply", "gemm_pool_kv", "pool_attention",
+    "inducer_chain", "gemm_unpool_q", "unpool_attention", "gemm_unpool_out", "gemm_mlp_up_act", "gemm_mlp_down",
+    "head_edm_step", "misc"};
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cls; size_t ev; double flops, bytes; };
+  std::vector<Rec> recs;
+  cudaEvent_t take() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+thread_local Profiler g_prof;
+inline void prof_begin(int cls, double flops, double bytes, cudaStream_t s) {
+  if (!g_prof.on) return;
+  g_prof.recs.push_back({cls, g_prof.used, flops, bytes});
+  cudaEventRecord(g_prof.take(), s);
+  g_prof.take();
+}
+inline void prof_end(cudaStream_t s) {
+  if (!g_prof.on) return;
+  cudaEventRecord(g_prof.pool[g_prof.recs.back().ev + 1], s);
+}
+}  // namespace
+}  // namespace gecco
 
 struct gecco_engine {
   gecco_model_desc d;
@@ -187,6 +231,14 @@ gecco_adagn_args adagn_base(const gecco_engine* e, const float* const* nw /* 4 p
     if (rc__ != 0) return rc__; \
   } while (0)
 
+#define TRYP(cls, flops, bytes, expr)   \
+  do {                                 \
+    prof_begin(cls, flops, bytes, s);  \
+    int rc__ = (expr);                 \
+    prof_end(s);                       \
+    if (rc__ != 0) return rc__;        \
+  } while (0)
+
 // One evaluation.  `xin` is the raw (un-scaled) [clouds, points, 3] input; the head arguments select what is
 // produced (see gecco_head_args modes).
 int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float* sigma, int sigma_stride, float sigma_imm,
@@ -197,6 +249,8 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
   const int sg = d.adagn_groups, Np = w.Np, rows = w.rows, irows = w.irows;
   const long long per_norm = (long long)clouds * sg * 2;
   const float sigma_data = t_embed ? 1.f : d.sigma_data;
+  // algorithmic work per launch (profiling only)
+  const double Mv = (double)clouds * points, Mi = (double)irows, Cd = C, Hd = hid;
   auto stat = [&](int layer, int which) { return w.stats + ((long long)layer * 4 + which) * per_norm; };
   double* head_stats = w.stats + 4LL * d.n_layers * per_norm;
   double* img_stats = head_stats + per_norm;
@@ -207,8 +261,10 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     int blocks = (int)((need + threads - 1) / threads);
     if (blocks > 1024) blocks = 1024;
     if ((long long)blocks * threads < clouds) blocks = ceil_div(clouds, threads);
+    prof_begin(K_PREP, 0, 8.0 * w.n_stats, s);
     prep_kernel<<<blocks, threads, 0, s>>>(w.stats, w.n_stats, sigma, sigma_stride, sigma_imm, t_embed, t_stride, clouds,
                                            w.sigma_eff, w.c_noise);
+    prof_end(s);
     GECCO_CHECK_LAUNCH("prep_kernel");
   }
 
@@ -220,7 +276,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     a.clouds = clouds; a.rows_per_cloud = Np; a.valid_rows = points; a.c = C;
     a.x = w.x; a.ldx = C;
     a.stats = stat(0, 0); a.stat_gs = C / sg;
-    TRY(launch_lift(a, s));
+    TRYP(K_LIFT, 6 * Mv * Cd, Mv * (Cd * 4 + 12), launch_lift(a, s));
   } else {  // RayNetwork: xyz_embed + img_feature_proj(lookup) (models/ray.py:99-113)
     int ctot = 0;
     gecco_lookup_args a = {};
@@ -238,9 +294,12 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     a.clouds = clouds; a.points = points; a.rows_per_cloud = Np;
     a.out_bf16 = w.big; a.ldo16 = ctot;
     a.stats = img_stats; a.stat_groups = d.img_groups;
-    TRY(launch_lookup(a, s));
-    TRY(launch_fold_gn(e->net[GECCO_NW_IMG_W], e->img_bias, img_stats, (double)points * (ctot / d.img_groups), 1e-5f,
-                       d.img_groups, ctot, C, clouds, w.wfold, ctot, w.bfold, s));
+    double pyr = 0;
+    for (int l = 0; l < d.n_levels; ++l) pyr += 2.0 * clouds * ctx.level_h[l] * ctx.level_w[l] * d.level_c[l];
+    TRYP(K_LOOKUP, 8 * Mv * ctot, pyr + Mv * (ctot * 2.0 + 12), launch_lookup(a, s));
+    TRYP(K_FOLD_GN, 2.0 * clouds * Cd * ctot, Cd * ctot * (4.0 + 2.0 * clouds),
+         launch_fold_gn(e->net[GECCO_NW_IMG_W], e->img_bias, img_stats, (double)points * (ctot / d.img_groups), 1e-5f,
+                        d.img_groups, ctot, C, clouds, w.wfold, ctot, w.bfold, s));
     gecco_gemm_args g = gemm_base(w.big, ctot, w.wfold, ctot, rows, C, ctot, Np, points);
     g.w_rows_per_cloud = C;
     g.bias = w.bfold; g.bias_stride = C;
@@ -248,7 +307,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     g.wx = e->net[GECCO_NW_EMBED_W];
     g.out_f32 = w.x; g.ldo32 = C;
     g.stats = stat(0, 0);
-    TRY(launch_gemm(g, s));
+    TRYP(K_GEMM_IMG, 2 * Mv * Cd * ctot + 6 * Mv * Cd, Mv * (ctot * 2.0 + Cd * 4) + 2.0 * clouds * Cd * ctot, launch_gemm(g, s));
   }
 
   // ---------------------------------------------------------------- SetTransformer (models/set_transformer.py:198-216)
@@ -259,13 +318,13 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     {
       gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_BN, w.x, stat(l, 0), w.c_noise, clouds, Np, points);
       a.out_bf16 = w.y; a.ldo16 = C;
-      TRY(launch_adagn(a, s));
+      TRYP(K_ADAGN, 2 * Mv * Cd, Mv * Cd * 6, launch_adagn(a, s));
     }
     if (cache_in == nullptr) {
       // AttentionPool (:47-65)
       gecco_gemm_args g = gemm_base(w.y, C, L.pool_kv_w, C, rows, 2 * C, C, Np, points);
       g.out_bf16 = w.big; g.ldo16 = 2 * C;
-      TRY(launch_gemm(g, s));
+      TRYP(K_GEMM_POOL_KV, 4 * Mv * Cd * Cd, Mv * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
       gecco_pool_args p = {};
       p.kv = w.big; p.ld = 2 * C; p.k_off = 0; p.v_off = C;
       p.clouds = clouds; p.rows_per_cloud = Np; p.valid_rows = points;
@@ -273,29 +332,31 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       p.q_inducers = L.q_ind;
       p.splits = w.splits; p.partial = w.partial;
       p.out_bf16 = w.pooled; p.ldo = C;
-      TRY(launch_pool_attention(p, s));
+      TRYP(K_POOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 2, launch_pool_attention(p, s));
       g = gemm_base(w.pooled, C, L.pool_out_w, C, irows, C, C, I, I);
       g.out_f32 = w.h; g.ldo32 = C; g.stats = stat(l, 1);
-      TRY(launch_gemm(g, s));
+      TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd * Cd, Mi * Cd * 6 + 2 * Cd * Cd, launch_gemm(g, s));
       // h = norm_2(mlp(norm_1(h)))  (:108-110)
       gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_N1, w.h, stat(l, 1), w.c_noise, clouds, I, I);
       a.out_bf16 = w.hn; a.ldo16 = C;
-      TRY(launch_adagn(a, s));
+      TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd, Mi * Cd * 6, launch_adagn(a, s));
       g = gemm_base(w.hn, C, L.bmlp_w0, C, irows, hid, C, I, I);
       g.bias = lw[GECCO_LW_BMLP_B0]; g.act = 1; g.act_alpha = L.bmlp_alpha;
       g.out_bf16 = w.hh; g.ldo16 = hid;
-      TRY(launch_gemm(g, s));
+      TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd * Hd, Mi * (Cd + Hd) * 2 + 2 * Cd * Hd, launch_gemm(g, s));
       g = gemm_base(w.hh, hid, L.bmlp_w2, hid, irows, C, hid, I, I);
       g.bias = lw[GECCO_LW_BMLP_B2];
       g.out_f32 = w.h2; g.ldo32 = C; g.stats = stat(l, 2);
-      TRY(launch_gemm(g, s));
+      TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd * Hd, Mi * (Hd * 2 + Cd * 4) + 2 * Cd * Hd, launch_gemm(g, s));
       a = adagn_base(e, lw + GECCO_LW_N2, w.h2, stat(l, 2), w.c_noise, clouds, I, I);
       a.out_bf16 = w.h3; a.ldo16 = C;
       if (cache_out != nullptr) { a.out_f32 = cache_out + (size_t)l * irows * C; a.ldo32 = C; }
-      TRY(launch_adagn(a, s));
+      TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd, Mi * Cd * 6, launch_adagn(a, s));
     } else {
       const long long n = (long long)irows * C;
+      prof_begin(K_INDUCER_CHAIN, 0, Mi * Cd * 6, s);
       pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cache_in + (size_t)l * irows * C, w.h3, n, 1.0f);
+      prof_end(s);
       GECCO_CHECK_LAUNCH("pack_bf16_kernel(cache)");
     }
     // unpool = nn.MultiheadAttention(query=y, key=value=h)  (:112)
@@ -303,37 +364,37 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       gecco_gemm_args g = gemm_base(w.h3, C, L.kv_w, C, irows, 2 * C, C, I, I);
       g.bias = lw[GECCO_LW_UNPOOL_IN_B] + C;
       g.out_bf16 = w.khv; g.ldo16 = 2 * C;
-      TRY(launch_gemm(g, s));
+      TRYP(K_INDUCER_CHAIN, 4 * Mi * Cd * Cd, Mi * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
       g = gemm_base(w.y, C, L.q_w, C, rows, C, C, Np, points);
       g.bias = L.q_b;
       g.out_bf16 = w.q; g.ldo16 = C;
-      TRY(launch_gemm(g, s));
+      TRYP(K_GEMM_UNPOOL_Q, 2 * Mv * Cd * Cd, Mv * Cd * 4 + 2 * Cd * Cd, launch_gemm(g, s));
       gecco_unpool_args u = {};
       u.q = w.q; u.ldq = C; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
       u.clouds = clouds; u.rows_per_cloud = Np; u.heads = H; u.head_dim = hd; u.inducers = I;
       u.out_bf16 = w.y; u.ldo = C;
-      TRY(launch_unpool_attention(u, s));
+      TRYP(K_UNPOOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 4, launch_unpool_attention(u, s));
       // x = x + out_proj(attn)  (:164), statistics for mlp_norm
       g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);
       g.bias = lw[GECCO_LW_UNPOOL_OUT_B];
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
       g.stats = stat(l, 3);
-      TRY(launch_gemm(g, s));
+      TRYP(K_GEMM_UNPOOL_OUT, 2 * Mv * Cd * Cd, Mv * Cd * 10 + 2 * Cd * Cd, launch_gemm(g, s));
     }
     // x = x + mlp(AdaGN_mlp(x, t))  (:165-166), statistics for the next broadcast_norm / the head norm
     {
       gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_MN, w.x, stat(l, 3), w.c_noise, clouds, Np, points);
       a.out_bf16 = w.y; a.ldo16 = C;
-      TRY(launch_adagn(a, s));
+      TRYP(K_ADAGN, 2 * Mv * Cd, Mv * Cd * 6, launch_adagn(a, s));
       gecco_gemm_args g = gemm_base(w.y, C, L.mlp_w0, C, rows, hid, C, Np, points);
       g.bias = lw[GECCO_LW_MLP_B0]; g.act = 1; g.act_alpha = L.mlp_alpha;
       g.out_bf16 = w.big; g.ldo16 = hid;
-      TRY(launch_gemm(g, s));
+      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd + Hd) * 2 + 2 * Cd * Hd, launch_gemm(g, s));
       g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
       g.bias = lw[GECCO_LW_MLP_B2];
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
       g.stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
-      TRY(launch_gemm(g, s));
+      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 8) + 2 * Cd * Hd, launch_gemm(g, s));
     }
   }
 
@@ -344,7 +405,8 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
   head.w_out = e->net[GECCO_NW_OUT_W]; head.b_out = e->net[GECCO_NW_OUT_B];
   head.xin = xin;
   head.sigma = w.sigma_eff; head.sigma_stride = 1; head.sigma_data = sigma_data;
-  return launch_head(head, s);
+  TRYP(K_HEAD, 6 * Mv * Cd, Mv * (Cd * 4 + 60), launch_head(head, s));
+  return GECCO_OK;
 }
 
 int check_common(const gecco_engine* e, int clouds, int points, const gecco_context& ctx, const void* ws, long long ws_bytes) {
@@ -538,5 +600,40 @@ extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* s
   // the last step is Euler only: the result is x_next
   copy_f64_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(w.x_next, a->x_out, n3);
   GECCO_CHECK_LAUNCH("copy_f64_kernel");
+  return GECCO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+extern "C" int gecco_profile_start(void) {
+  g_prof.on = true;
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return GECCO_OK;
+}
+
+extern "C" int gecco_profile_stop(gecco_profile_entry* out, int32_t capacity, int32_t* count) {
+  g_prof.on = false;
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) return fail_cuda(ce, "gecco_profile_stop: cudaDeviceSynchronize");
+  gecco_profile_entry acc[K_COUNT];
+  memset(acc, 0, sizeof(acc));
+  for (int i = 0; i < K_COUNT; ++i) strncpy(acc[i].name, kClassNames[i], sizeof(acc[i].name) - 1);
+  for (const Profiler::Rec& r : g_prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.pool[r.ev], g_prof.pool[r.ev + 1]) != cudaSuccess) continue;
+    acc[r.cls].launches += 1;
+    acc[r.cls].ms += ms;
+    acc[r.cls].flops += r.flops;
+    acc[r.cls].bytes += r.bytes;
+  }
+  g_prof.recs.clear();
+  g_prof.used = 0;
+  int n = 0;
+  for (int i = 0; i < K_COUNT; ++i) {
+    if (acc[i].launches == 0) continue;
+    if (out != nullptr && n < capacity) out[n] = acc[i];
+    ++n;
+  }
+  if (count != nullptr) *count = n;
   return GECCO_OK;
 }

@@ -188,7 +188,12 @@ class Diffusion(_Base):
         ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])
         gammas = self._gammas(ts, num_steps, kw["S_churn"], kw["S_min"], kw["S_max"])
         # one draw per step, even where gamma is 0 (diffusion.py:324)
-        noise = torch.stack([self._randn(latents.shape, rng, device, dtype) for _ in range(num_steps)])
+        noise = torch.empty((num_steps, *latents.shape), device=device, dtype=dtype)
+        for i in range(num_steps):
+            if rng.device == device:
+                noise[i].normal_(generator=rng)  # == torch.randn(shape, generator=rng) written in place
+            else:
+                noise[i].copy_(self._randn(latents.shape, rng, device, dtype))
         net, sigma_data = self._network()
         x = engine_for(net, sigma_data).sample(latents, noise, ts.tolist(), gammas, kw["S_noise"], post_context=post_context,
                                                K=None if context is None else context.K)

@@ -294,3 +294,22 @@ def engine_for(network: torch.nn.Module, sigma_data: float = 1.0) -> Engine:
     if key not in cache:
         cache[key] = Engine(network, sigma_data)
     return cache[key]
+
+
+def profile_start() -> None:
+    """Starts per-kernel-class device timing of every engine launch on this thread (gecco_profile_start)."""
+    _abi.check(_abi.load().gecco_profile_start())
+
+
+def profile_stop() -> list[dict]:
+    """Stops the timing, synchronises, and returns [{name, launches, ms, flops, bytes}] per kernel class."""
+    buf = (_abi.ProfileEntry * 32)()
+    n = C.c_int32(0)
+    _abi.check(_abi.load().gecco_profile_stop(buf, 32, C.byref(n)))
+    return [dict(name=buf[i].name.decode(), launches=int(buf[i].launches), ms=float(buf[i].ms), flops=float(buf[i].flops),
+                 bytes=float(buf[i].bytes)) for i in range(min(n.value, 32))]
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernel launches issued by the library on this thread since the last reset (gecco_launch_count)."""
+    return int(_abi.load().gecco_launch_count(C.c_int32(1 if reset else 0)))

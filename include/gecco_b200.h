@@ -321,6 +321,17 @@ typedef struct gecco_sample_args {
 } gecco_sample_args;
 int gecco_sample(gecco_engine* e, const gecco_sample_args* args, void* stream);
 
+/* Per-kernel-class device timing of the engine (tracing aid; the reference has none).  Between
+ * start and stop every engine launch on this thread is bracketed by CUDA events on its stream; stop synchronises
+ * the device and returns, per class, the launch count, summed device time and the algorithmic FLOPs / bytes. */
+typedef struct gecco_profile_entry {
+  char name[32];
+  int64_t launches;
+  double ms, flops, bytes;
+} gecco_profile_entry;
+int gecco_profile_start(void);
+int gecco_profile_stop(gecco_profile_entry* out, int32_t capacity, int32_t* count);
+
 /* Number of kernel launches the library has issued on this thread since the last call (bench bookkeeping). */
 int64_t gecco_launch_count(int32_t reset);
 
