@@ -57,7 +57,22 @@ class LiftArgs(C.Structure):
         ("w", C.c_void_p), ("b", C.c_void_p),
         ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32), ("valid_rows", C.c_int32), ("c", C.c_int32),
         ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("x_bf16", C.c_void_p), ("ldxb", C.c_int64),
         ("stats", C.c_void_p), ("stat_gs", C.c_int32),
+    ]
+
+
+class FoldAdaGNArgs(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("n_out", C.c_int32), ("c", C.c_int32),
+        ("stats", C.c_void_p), ("stat_gs", C.c_int32), ("groups", C.c_int32), ("valid_rows", C.c_int32), ("eps", C.c_float),
+        ("t", C.c_void_p), ("t_stride", C.c_int32), ("ctx_dim", C.c_int32),
+        ("scale_w", C.c_void_p), ("scale_b", C.c_void_p), ("bias_w", C.c_void_p), ("bias_b", C.c_void_p),
+        ("clouds", C.c_int32),
+        ("w_folded_bf16", C.c_void_p), ("ldwf", C.c_int64), ("wf_cloud_stride", C.c_int64),
+        ("bias_folded", C.c_void_p), ("bias_stride", C.c_int32),
     ]
 
 

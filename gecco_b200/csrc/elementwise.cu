@@ -115,6 +115,55 @@ __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// AdaGN followed by a Linear, folded per cloud (models/normalization.py:36-44 + the consumer nn.Linear):
+//   AdaGN(x)[c] = a[c] x[c] + s[c],  a = scale(t) rstd_g,  s = bias(t) - a mean_g
+//   Linear(AdaGN(x))[o] = sum_c (W[o,c] a[c]) x[c] + (b[o] + sum_c W[o,c] s[c])
+// so the consumer GEMM reads the bf16 residual stream directly with per-cloud weights.  grid (row blocks, clouds),
+// 128 threads; a warp owns whole output rows (coalesced fp32 reads, 8 B bf16 writes, shuffle-reduced bias dot).
+constexpr int FOLD_ROWS = 32;
+constexpr int FOLD_MAXC = 1024;
+
+__global__ void __launch_bounds__(128)
+fold_adagn_kernel(const float* __restrict__ W, long long ldw, const float* __restrict__ bias, int n_out, int C,
+                  const double* __restrict__ stats, int stat_gs, int groups, double count, float eps,
+                  const float* __restrict__ t, int t_stride, const float* __restrict__ scale_w,
+                  const float* __restrict__ scale_b, const float* __restrict__ bias_w, const float* __restrict__ bias_b,
+                  __nv_bfloat16* __restrict__ wf, long long ldwf, long long wf_cloud_stride, float* __restrict__ bf,
+                  int bf_stride) {
+  __shared__ __align__(16) float sa[FOLD_MAXC];
+  __shared__ __align__(16) float ss[FOLD_MAXC];
+  const int cloud = blockIdx.y;
+  const int gs = C / groups;
+  const double* cstats = stats + (long long)cloud * (C / stat_gs) * 2;
+  const float tc = __ldg(t + (long long)cloud * t_stride);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    group_mean_rstd(cstats, c / gs, gs, stat_gs, count, eps, mean, rstd);
+    const float sc = tc * __ldg(scale_w + c) + __ldg(scale_b + c);
+    const float bi = tc * __ldg(bias_w + c) + __ldg(bias_b + c);
+    sa[c] = sc * rstd;
+    ss[c] = bi - sc * rstd * mean;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o_end = min((int)(blockIdx.x + 1) * FOLD_ROWS, n_out);
+  for (int o = blockIdx.x * FOLD_ROWS + warp; o < o_end; o += 4) {
+    const float* wr = W + (long long)o * ldw;
+    __nv_bfloat16* dst = wf + (long long)cloud * wf_cloud_stride + (long long)o * ldwf;
+    float dot = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wr + c));
+      const float4 a = *reinterpret_cast<const float4*>(sa + c);
+      const float4 sv = *reinterpret_cast<const float4*>(ss + c);
+      dot += w.x * sv.x + w.y * sv.y + w.z * sv.z + w.w * sv.w;
+      *reinterpret_cast<uint2*>(dst + c) = make_uint2(pack_bf16x2(w.x * a.x, w.y * a.y), pack_bf16x2(w.z * a.z, w.w * a.w));
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) bf[(long long)cloud * bf_stride + o] = dot + (bias != nullptr ? __ldg(bias + o) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Unconditional lift (models/linear_lift.py:21,44): x = W (c_in * xin) + b, plus AdaGN statistics of x
 // at `gs`-channel granularity.  Padding rows are written as 0.
 constexpr int LIFT_ROWS = 32;
@@ -122,7 +171,7 @@ constexpr int LIFT_ROWS = 32;
 __global__ void lift_kernel(const float* __restrict__ xin, const float* __restrict__ sigma, int sigma_stride,
                             float sigma_data, const float* __restrict__ w, const float* __restrict__ b,
                             int rows_per_cloud, int valid_rows, int C, int gs, float* __restrict__ x, long long ldx,
-                            double* __restrict__ stats) {
+                            __nv_bfloat16* __restrict__ xb, long long ldxb, double* __restrict__ stats) {
   extern __shared__ float sgrp[];
   const int ngroups = C / gs;
   for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.f;
@@ -160,6 +209,8 @@ __global__ void lift_kernel(const float* __restrict__ xin, const float* __restri
         }
       }
       *reinterpret_cast<float4*>(x + (row_base + r) * ldx + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      if (xb != nullptr)
+        *reinterpret_cast<uint2*>(xb + (row_base + r) * ldxb + cq * 4) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
     }
     if (stats != nullptr) {
 #pragma unroll
@@ -380,15 +431,32 @@ int launch_adagn(const gecco_adagn_args& a, cudaStream_t s) {
   return GECCO_OK;
 }
 
+int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s) {
+  GECCO_REQUIRE(a.w && a.stats && a.t && a.w_folded_bf16 && a.bias_folded, "fold_adagn: null argument");
+  GECCO_REQUIRE(a.c % 4 == 0 && a.c <= FOLD_MAXC && a.ldw % 4 == 0 && a.ldwf % 4 == 0, "fold_adagn: C must be a multiple of 4 (<= %d)", FOLD_MAXC);
+  GECCO_REQUIRE(a.groups > 0 && a.c % a.groups == 0 && a.stat_gs > 0 && (a.c / a.groups) % a.stat_gs == 0,
+                "fold_adagn: group size must be a multiple of the statistics granularity");
+  GECCO_REQUIRE(a.ctx_dim == 1, "fold_adagn: t_embed_dim must be 1");
+  if (a.n_out == 0 || a.clouds == 0) return GECCO_OK;
+  dim3 grid(ceil_div(a.n_out, FOLD_ROWS), a.clouds);
+  fold_adagn_kernel<<<grid, 128, 0, s>>>(a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
+                                        (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b,
+                                        a.bias_w, a.bias_b, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf,
+                                        a.wf_cloud_stride, a.bias_folded, a.bias_stride);
+  GECCO_CHECK_LAUNCH("fold_adagn_kernel");
+  return GECCO_OK;
+}
+
 int launch_lift(const gecco_lift_args& a, cudaStream_t s) {
   GECCO_REQUIRE(a.c % 4 == 0 && a.ldx % 4 == 0, "lift: bad channel layout");
+  GECCO_REQUIRE(!a.x_bf16 || a.ldxb % 4 == 0, "lift: bf16 leading dimension must be a multiple of 4");
   GECCO_REQUIRE(!a.stats || (a.stat_gs > 0 && a.c % a.stat_gs == 0), "lift: bad statistics granularity");
   dim3 grid(ceil_div(a.rows_per_cloud, LIFT_ROWS), a.clouds);
   const int threads = a.c / 4 < 256 ? ((a.c / 4 + 31) / 32) * 32 : 256;
   const int gs = a.stats ? a.stat_gs : a.c;
   lift_kernel<<<grid, threads, (a.c / gs) * 2 * sizeof(float), s>>>(a.xin, a.sigma, a.sigma_stride, a.sigma_data, a.w, a.b,
                                                                    a.rows_per_cloud, a.valid_rows, a.c, gs, a.x, a.ldx,
-                                                                   a.stats);
+                                                                   static_cast<__nv_bfloat16*>(a.x_bf16), a.ldxb, a.stats);
   GECCO_CHECK_LAUNCH("lift_kernel");
   return GECCO_OK;
 }
@@ -429,6 +497,11 @@ extern "C" int gecco_group_stats(const float* x, int64_t ldx, int32_t clouds, in
 extern "C" int gecco_adagn(const gecco_adagn_args* a, void* stream) {
   if (!a) { gecco::set_error("gecco_adagn: null args"); return GECCO_ERR_INVALID; }
   return gecco::launch_adagn(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_fold_adagn(const gecco_fold_adagn_args* a, void* stream) {
+  if (!a) { gecco::set_error("gecco_fold_adagn: null args"); return GECCO_ERR_INVALID; }
+  return gecco::launch_fold_adagn(*a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gecco_lift(const gecco_lift_args* a, void* stream) {

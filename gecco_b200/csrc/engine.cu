@@ -17,12 +17,12 @@
 namespace gecco {
 namespace {
 enum KClass {
-  K_PREP = 0, K_LIFT, K_LOOKUP, K_FOLD_GN, K_GEMM_IMG, K_ADAGN, K_GEMM_POOL_KV, K_POOL_ATTN, K_INDUCER_CHAIN,
-  K_GEMM_UNPOOL_Q, K_UNPOOL_ATTN, K_GEMM_UNPOOL_OUT, K_GEMM_MLP0, K_GEMM_MLP2, K_HEAD, K_MISC, K_COUNT
+  K_PREP = 0, K_LIFT, K_LOOKUP, K_FOLD_GN, K_GEMM_IMG, K_FOLD_ADAGN, K_GEMM_KVQ, K_POOL_ATTN, K_INDUCER_CHAIN,
+  K_UNPOOL_ATTN, K_GEMM_UNPOOL_OUT, K_GEMM_MLP0, K_GEMM_MLP2, K_HEAD, K_MISC, K_COUNT
 };
 const char* const kClassNames[K_COUNT] = {
-    "prep", "lift", "lookup", "fold_group_norm", "gemm_img_proj", "adagn_apply", "gemm_pool_kv", "pool_attention",
-    "inducer_chain", "gemm_unpool_q", "unpool_attention", "gemm_unpool_out", "gemm_mlp_up_act", "gemm_mlp_down",
+    "prep", "lift", "lookup", "fold_group_norm", "gemm_img_proj", "fold_adagn", "gemm_kv_q", "pool_attention",
+    "inducer_chain", "unpool_attention", "gemm_unpool_out", "gemm_mlp_up_act", "gemm_mlp_down",
     "head_edm_step", "misc"};
 struct Profiler {
   bool on = false;
@@ -61,8 +61,9 @@ struct gecco_engine {
   std::vector<const float*> lw;  // [n_layers * GECCO_LW_COUNT]
   // packed (owned)
   struct Layer {
-    __nv_bfloat16 *pool_kv_w, *pool_out_w, *bmlp_w0, *bmlp_w2, *q_w, *kv_w, *out_w, *mlp_w0, *mlp_w2, *q_ind;
-    float* q_b;
+    __nv_bfloat16 *pool_out_w, *bmlp_w0, *bmlp_w2, *kv_w, *out_w, *mlp_w2, *q_ind;
+    // fp32 sources of the AdaGN-folded projections: [kv_proj.weight ; qscale * in_proj_weight[0:C]] and its bias
+    float *wcat, *bcat;
     float bmlp_alpha, mlp_alpha;
   };
   std::vector<Layer> layers;
@@ -128,10 +129,11 @@ struct Carver {
 
 struct Workspace {
   int Np, rows, irows, splits;
-  float* x;            // [rows, C] residual stream
-  __nv_bfloat16* y;    // [rows, C] normalised operand / attention output
-  __nv_bfloat16* big;  // [rows, max(2C, hidden, sum level_c)] kv | mlp hidden | looked-up image features
-  __nv_bfloat16* q;    // [rows, C]
+  float* x;            // [rows, C] residual stream (fp32)
+  __nv_bfloat16* xb;   // [rows, C] bf16 copy of the residual stream: the operand of the AdaGN-folded projections
+  __nv_bfloat16* y;    // [rows, C] unpool attention output
+  __nv_bfloat16* big;  // [rows, max(3C, hidden, sum level_c)] k|v|q | mlp hidden | looked-up image features
+  int wide;
   __nv_bfloat16 *pooled, *hn, *hh, *h3, *khv;
   float *h, *h2, *partial;
   double* stats;
@@ -161,14 +163,15 @@ Workspace carve(const gecco_engine* e, int clouds, int points, void* base) {
   w.rows = clouds * w.Np;
   w.irows = clouds * I;
   w.splits = pool_splits(clouds, d.num_heads, ceil_div(points, 64));
-  int wide = 2 * C;
+  int wide = 3 * C;
   if (hid > wide) wide = hid;
   if (ctx > wide) wide = ctx;
+  w.wide = wide;
   Carver c{static_cast<uint8_t*>(base)};
   w.x = c.take<float>((size_t)w.rows * C);
+  w.xb = c.take<__nv_bfloat16>((size_t)w.rows * C);
   w.y = c.take<__nv_bfloat16>((size_t)w.rows * C);
   w.big = c.take<__nv_bfloat16>((size_t)w.rows * wide);
-  w.q = c.take<__nv_bfloat16>((size_t)w.rows * C);
   w.pooled = c.take<__nv_bfloat16>((size_t)w.irows * C);
   w.hn = c.take<__nv_bfloat16>((size_t)w.irows * C);
   w.hh = c.take<__nv_bfloat16>((size_t)w.irows * hid);
@@ -184,12 +187,12 @@ Workspace carve(const gecco_engine* e, int clouds, int points, void* base) {
   w.stats = c.take<double>((size_t)w.n_stats);
   w.sigma_eff = c.take<float>(clouds);
   w.c_noise = c.take<float>(clouds);
-  if (d.kind == 1) {
-    w.wfold = c.take<__nv_bfloat16>((size_t)clouds * C * ctx);
-    w.bfold = c.take<float>((size_t)clouds * C);
-  } else {
-    w.wfold = nullptr;
-    w.bfold = nullptr;
+  {
+    size_t wf = (size_t)3 * C * C;  // [k|v|q] projections folded with broadcast_norm
+    if ((size_t)hid * C > wf) wf = (size_t)hid * C;  // mlp.0 folded with mlp_norm
+    if ((size_t)C * ctx > wf) wf = (size_t)C * ctx;  // img_feature_proj folded with its GroupNorm
+    w.wfold = c.take<__nv_bfloat16>((size_t)clouds * wf);
+    w.bfold = c.take<float>((size_t)clouds * (3 * C > hid ? 3 * C : hid));
   }
   const size_t n3 = (size_t)clouds * points * 3;
   w.x_hat = c.take<double>(n3);
@@ -222,6 +225,18 @@ gecco_adagn_args adagn_base(const gecco_engine* e, const float* const* nw /* 4 p
   a.clouds = clouds; a.rows_per_cloud = rows_per_cloud; a.valid_rows = valid_rows; a.c = C;
   a.groups = e->d.adagn_groups;
   a.eps = 1e-5f;
+  return a;
+}
+
+gecco_fold_adagn_args fold_base(const gecco_engine* e, const float* const* nw /* 4 pointers */, const double* stats,
+                                const float* t, int clouds, int valid_rows) {
+  gecco_fold_adagn_args a = {};
+  a.c = e->d.feature_dim;
+  a.stats = stats; a.stat_gs = a.c / e->d.adagn_groups; a.groups = e->d.adagn_groups; a.valid_rows = valid_rows;
+  a.eps = 1e-5f;
+  a.t = t; a.t_stride = 1; a.ctx_dim = 1;
+  a.scale_w = nw[0]; a.scale_b = nw[1]; a.bias_w = nw[2]; a.bias_b = nw[3];
+  a.clouds = clouds;
   return a;
 }
 
@@ -269,14 +284,16 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
   }
 
   // ---------------------------------------------------------------- input embedding
+  // Both paths write the fp32 residual stream x, its bf16 copy xb and the statistics of the first AdaGN.
   if (d.kind == 0) {  // LinearLift.lift (models/linear_lift.py:44)
     gecco_lift_args a = {};
     a.xin = xin; a.sigma = w.sigma_eff; a.sigma_stride = 1; a.sigma_data = sigma_data;
     a.w = e->net[GECCO_NW_EMBED_W]; a.b = e->net[GECCO_NW_EMBED_B];
     a.clouds = clouds; a.rows_per_cloud = Np; a.valid_rows = points; a.c = C;
     a.x = w.x; a.ldx = C;
+    a.x_bf16 = w.xb; a.ldxb = C;
     a.stats = stat(0, 0); a.stat_gs = C / sg;
-    TRYP(K_LIFT, 6 * Mv * Cd, Mv * (Cd * 4 + 12), launch_lift(a, s));
+    TRYP(K_LIFT, 6 * Mv * Cd, Mv * (Cd * 6 + 12), launch_lift(a, s));
   } else {  // RayNetwork: xyz_embed + img_feature_proj(lookup) (models/ray.py:99-113)
     int ctot = 0;
     gecco_lookup_args a = {};
@@ -306,34 +323,43 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     g.geom = xin; g.sigma = w.sigma_eff; g.sigma_stride = 1; g.sigma_data = sigma_data;
     g.wx = e->net[GECCO_NW_EMBED_W];
     g.out_f32 = w.x; g.ldo32 = C;
+    g.out_bf16 = w.xb; g.ldo16 = C;
     g.stats = stat(0, 0);
-    TRYP(K_GEMM_IMG, 2 * Mv * Cd * ctot + 6 * Mv * Cd, Mv * (ctot * 2.0 + Cd * 4) + 2.0 * clouds * Cd * ctot, launch_gemm(g, s));
+    TRYP(K_GEMM_IMG, 2 * Mv * Cd * ctot + 6 * Mv * Cd, Mv * (ctot * 2.0 + Cd * 6) + 2.0 * clouds * Cd * ctot, launch_gemm(g, s));
   }
 
   // ---------------------------------------------------------------- SetTransformer (models/set_transformer.py:198-216)
+  const int C3 = 3 * C;
   for (int l = 0; l < d.n_layers; ++l) {
     const gecco_engine::Layer& L = e->layers[l];
     const float* const* lw = e->lw.data() + (size_t)l * GECCO_LW_COUNT;
-    // y = AdaGN_bn(x, t)  (:162)
+    // y = AdaGN_bn(x, t) (:162) is never materialised: it is folded into the per-cloud weights of its two consumers,
+    // AttentionPool.kv_proj (:49) and the unpool query projection (:112), which then read xb directly.
+    const bool pooling = cache_in == nullptr;
+    const int r0 = pooling ? 0 : 2 * C;  // the cached pass only needs the q rows
     {
-      gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_BN, w.x, stat(l, 0), w.c_noise, clouds, Np, points);
-      a.out_bf16 = w.y; a.ldo16 = C;
-      TRYP(K_ADAGN, 2 * Mv * Cd, Mv * Cd * 6, launch_adagn(a, s));
+      gecco_fold_adagn_args f = fold_base(e, lw + GECCO_LW_BN, stat(l, 0), w.c_noise, clouds, points);
+      f.w = L.wcat + (size_t)r0 * C; f.ldw = C; f.bias = L.bcat + r0; f.n_out = C3 - r0;
+      f.w_folded_bf16 = w.wfold + (size_t)r0 * C; f.ldwf = C; f.wf_cloud_stride = (long long)C3 * C;
+      f.bias_folded = w.bfold + r0; f.bias_stride = C3;
+      TRYP(K_FOLD_ADAGN, 2.0 * clouds * (C3 - r0) * Cd, (C3 - r0) * Cd * (4.0 + 2.0 * clouds), launch_fold_adagn(f, s));
+      gecco_gemm_args g = gemm_base(w.xb, C, w.wfold + (size_t)r0 * C, C, rows, C3 - r0, C, Np, points);
+      g.w_rows_per_cloud = C3;
+      g.bias = w.bfold + r0; g.bias_stride = C3;
+      g.out_bf16 = w.big + r0; g.ldo16 = C3;
+      TRYP(K_GEMM_KVQ, 2 * Mv * Cd * (C3 - r0), Mv * (Cd * 2 + (C3 - r0) * 2.0) + 2.0 * clouds * (C3 - r0) * Cd, launch_gemm(g, s));
     }
-    if (cache_in == nullptr) {
+    if (pooling) {
       // AttentionPool (:47-65)
-      gecco_gemm_args g = gemm_base(w.y, C, L.pool_kv_w, C, rows, 2 * C, C, Np, points);
-      g.out_bf16 = w.big; g.ldo16 = 2 * C;
-      TRYP(K_GEMM_POOL_KV, 4 * Mv * Cd * Cd, Mv * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
       gecco_pool_args p = {};
-      p.kv = w.big; p.ld = 2 * C; p.k_off = 0; p.v_off = C;
+      p.kv = w.big; p.ld = C3; p.k_off = 0; p.v_off = C;
       p.clouds = clouds; p.rows_per_cloud = Np; p.valid_rows = points;
       p.heads = H; p.head_dim = hd; p.inducers = I;
       p.q_inducers = L.q_ind;
       p.splits = w.splits; p.partial = w.partial;
       p.out_bf16 = w.pooled; p.ldo = C;
       TRYP(K_POOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 2, launch_pool_attention(p, s));
-      g = gemm_base(w.pooled, C, L.pool_out_w, C, irows, C, C, I, I);
+      gecco_gemm_args g = gemm_base(w.pooled, C, L.pool_out_w, C, irows, C, C, I, I);
       g.out_f32 = w.h; g.ldo32 = C; g.stats = stat(l, 1);
       TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd * Cd, Mi * Cd * 6 + 2 * Cd * Cd, launch_gemm(g, s));
       // h = norm_2(mlp(norm_1(h)))  (:108-110)
@@ -365,36 +391,38 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       g.bias = lw[GECCO_LW_UNPOOL_IN_B] + C;
       g.out_bf16 = w.khv; g.ldo16 = 2 * C;
       TRYP(K_INDUCER_CHAIN, 4 * Mi * Cd * Cd, Mi * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
-      g = gemm_base(w.y, C, L.q_w, C, rows, C, C, Np, points);
-      g.bias = L.q_b;
-      g.out_bf16 = w.q; g.ldo16 = C;
-      TRYP(K_GEMM_UNPOOL_Q, 2 * Mv * Cd * Cd, Mv * Cd * 4 + 2 * Cd * Cd, launch_gemm(g, s));
       gecco_unpool_args u = {};
-      u.q = w.q; u.ldq = C; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
+      u.q = w.big + 2 * C; u.ldq = C3; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
       u.clouds = clouds; u.rows_per_cloud = Np; u.heads = H; u.head_dim = hd; u.inducers = I;
       u.out_bf16 = w.y; u.ldo = C;
       TRYP(K_UNPOOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 4, launch_unpool_attention(u, s));
-      // x = x + out_proj(attn)  (:164), statistics for mlp_norm
+      // x = x + out_proj(attn)  (:164), bf16 copy, statistics for mlp_norm
       g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);
       g.bias = lw[GECCO_LW_UNPOOL_OUT_B];
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
+      g.out_bf16 = w.xb; g.ldo16 = C;
       g.stats = stat(l, 3);
-      TRYP(K_GEMM_UNPOOL_OUT, 2 * Mv * Cd * Cd, Mv * Cd * 10 + 2 * Cd * Cd, launch_gemm(g, s));
+      TRYP(K_GEMM_UNPOOL_OUT, 2 * Mv * Cd * Cd, Mv * Cd * 12 + 2 * Cd * Cd, launch_gemm(g, s));
     }
-    // x = x + mlp(AdaGN_mlp(x, t))  (:165-166), statistics for the next broadcast_norm / the head norm
+    // x = x + mlp(AdaGN_mlp(x, t))  (:165-166): mlp_norm folded into mlp.0; statistics for the next broadcast_norm /
+    // the head norm
     {
-      gecco_adagn_args a = adagn_base(e, lw + GECCO_LW_MN, w.x, stat(l, 3), w.c_noise, clouds, Np, points);
-      a.out_bf16 = w.y; a.ldo16 = C;
-      TRYP(K_ADAGN, 2 * Mv * Cd, Mv * Cd * 6, launch_adagn(a, s));
-      gecco_gemm_args g = gemm_base(w.y, C, L.mlp_w0, C, rows, hid, C, Np, points);
-      g.bias = lw[GECCO_LW_MLP_B0]; g.act = 1; g.act_alpha = L.mlp_alpha;
+      gecco_fold_adagn_args f = fold_base(e, lw + GECCO_LW_MN, stat(l, 3), w.c_noise, clouds, points);
+      f.w = lw[GECCO_LW_MLP_W0]; f.ldw = C; f.bias = lw[GECCO_LW_MLP_B0]; f.n_out = hid;
+      f.w_folded_bf16 = w.wfold; f.ldwf = C; f.wf_cloud_stride = (long long)hid * C;
+      f.bias_folded = w.bfold; f.bias_stride = hid;
+      TRYP(K_FOLD_ADAGN, 2.0 * clouds * Hd * Cd, Hd * Cd * (4.0 + 2.0 * clouds), launch_fold_adagn(f, s));
+      gecco_gemm_args g = gemm_base(w.xb, C, w.wfold, C, rows, hid, C, Np, points);
+      g.w_rows_per_cloud = hid;
+      g.bias = w.bfold; g.bias_stride = hid; g.act = 1; g.act_alpha = L.mlp_alpha;
       g.out_bf16 = w.big; g.ldo16 = hid;
-      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd + Hd) * 2 + 2 * Cd * Hd, launch_gemm(g, s));
+      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd + Hd) * 2 + 2.0 * clouds * Cd * Hd, launch_gemm(g, s));
       g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
       g.bias = lw[GECCO_LW_MLP_B2];
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
+      g.out_bf16 = w.xb; g.ldo16 = C;
       g.stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
-      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 8) + 2 * Cd * Hd, launch_gemm(g, s));
+      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 10) + 2 * Cd * Hd, launch_gemm(g, s));
     }
   }
 
@@ -475,10 +503,13 @@ extern "C" int gecco_create(const gecco_model_desc* desc, const float* const* ne
   e->lw.assign(layer_weights, layer_weights + (size_t)d.n_layers * GECCO_LW_COUNT);
   e->layers.resize(d.n_layers);
 
-  const size_t per_layer_bf16 = (size_t)2 * C * C + (size_t)C * C + 2 * (size_t)hid * C + (size_t)C * C + (size_t)2 * C * C +
-                                (size_t)C * C + 2 * (size_t)hid * C + (size_t)H * I * (C / H);
+  // bf16: pool out_proj, inducer mlp (2), unpool k/v in-proj, unpool out_proj, mlp.2, inducer queries
+  const size_t per_layer_bf16 = (size_t)C * C + 2 * (size_t)hid * C + (size_t)2 * C * C + (size_t)C * C + (size_t)hid * C +
+                                (size_t)H * I * (C / H);
+  // fp32: [kv_proj ; q in-proj] weight and bias (sources of the AdaGN fold)
+  const size_t per_layer_f32 = (size_t)3 * C * C + (size_t)3 * C;
   size_t bytes = 0;
-  for (int l = 0; l < d.n_layers; ++l) bytes += align_up(per_layer_bf16 * 2 + 64 * 16) + align_up((size_t)C * 4);
+  for (int l = 0; l < d.n_layers; ++l) bytes += align_up(per_layer_bf16 * 2 + 64 * 16) + align_up(per_layer_f32 * 4 + 64 * 16);
   bytes += align_up((size_t)C * 4) + 4096;
   ce = cudaMalloc(&e->arena, bytes);
   if (ce != cudaSuccess) {
@@ -499,18 +530,20 @@ extern "C" int gecco_create(const gecco_model_desc* desc, const float* const* ne
   for (int l = 0; l < d.n_layers; ++l) {
     const float* const* lw = layer_weights + (size_t)l * GECCO_LW_COUNT;
     gecco_engine::Layer& L = e->layers[l];
-    L.pool_kv_w = pack(lw[GECCO_LW_POOL_KV_W], (size_t)2 * C * C, 1.f);
     L.pool_out_w = pack(lw[GECCO_LW_POOL_OUT_W], (size_t)C * C, 1.f);
     L.bmlp_w0 = pack(lw[GECCO_LW_BMLP_W0], (size_t)hid * C, 1.f);
     L.bmlp_w2 = pack(lw[GECCO_LW_BMLP_W2], (size_t)C * hid, 1.f);
-    L.q_w = pack(lw[GECCO_LW_UNPOOL_IN_W], (size_t)C * C, qscale);                       // in_proj_weight[0:C]
     L.kv_w = pack(lw[GECCO_LW_UNPOOL_IN_W] + (size_t)C * C, (size_t)2 * C * C, 1.f);      // in_proj_weight[C:3C]
     L.out_w = pack(lw[GECCO_LW_UNPOOL_OUT_W], (size_t)C * C, 1.f);
-    L.mlp_w0 = pack(lw[GECCO_LW_MLP_W0], (size_t)hid * C, 1.f);
     L.mlp_w2 = pack(lw[GECCO_LW_MLP_W2], (size_t)C * hid, 1.f);
     L.q_ind = pack(lw[GECCO_LW_INDUCERS], (size_t)H * I * (C / H), qscale);
-    L.q_b = c.take<float>(C);
-    scale_add_f32_kernel<<<ceil_div(C, 256), 256, 0, s>>>(lw[GECCO_LW_UNPOOL_IN_B], nullptr, L.q_b, C, qscale);
+    // [kv_proj.weight (2C rows, no bias) ; qscale * in_proj_weight[0:C] (bias qscale * in_proj_bias[0:C])]
+    L.wcat = c.take<float>((size_t)3 * C * C);
+    L.bcat = c.take<float>((size_t)3 * C);
+    scale_add_f32_kernel<<<ceil_div(2 * C * C, 256), 256, 0, s>>>(lw[GECCO_LW_POOL_KV_W], nullptr, L.wcat, 2 * C * C, 1.f);
+    scale_add_f32_kernel<<<ceil_div(C * C, 256), 256, 0, s>>>(lw[GECCO_LW_UNPOOL_IN_W], nullptr, L.wcat + (size_t)2 * C * C, C * C, qscale);
+    cudaMemsetAsync(L.bcat, 0, (size_t)2 * C * sizeof(float), s);
+    scale_add_f32_kernel<<<ceil_div(C, 256), 256, 0, s>>>(lw[GECCO_LW_UNPOOL_IN_B], nullptr, L.bcat + 2 * C, C, qscale);
     cudaMemcpyAsync(&alphas[2 * l], lw[GECCO_LW_BMLP_ALPHA], sizeof(float), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(&alphas[2 * l + 1], lw[GECCO_LW_MLP_ALPHA], sizeof(float), cudaMemcpyDeviceToHost, s);
   }

@@ -1,12 +1,14 @@
-// Persistent, warp-specialised tcgen05 GEMM with a fused epilogue (gecco_gemm).
+// Persistent, warp-specialised tcgen05 GEMM with a fused, TMA-staged epilogue (gecco_gemm).
 //
 //   warp 0 : TMA producer  (A tile 128x64 + W tile 192x64 bf16 per stage, SWIZZLE_128B)
 //   warp 1 : MMA issuer    (one thread; 4 x tcgen05.mma M=128 N=192 K=16 per stage)
 //   warp 2 : TMEM allocator (512 columns = two 192-wide fp32 accumulator slots)
-//   warps 4-7 : epilogue   (tcgen05.ld -> bias / xyz-embed / activation / residual /
-//                           AdaGN statistics -> fp32 and/or bf16 stores)
+//   warp 3 : residual loader (TMA prefetch of the fp32 residual chunks the epilogue will add)
+//   warps 4-7 : epilogue   (epilogue.cuh: tcgen05.ld -> bias / xyz-embed / activation / residual /
+//                           AdaGN statistics -> swizzled smem staging -> TMA bulk stores, fp32 and/or bf16)
 // The two TMEM slots let the epilogue of tile i overlap the main loop of tile i+1.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
@@ -19,50 +21,41 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 192;
 constexpr int BK = 64;
-constexpr int STAGES = 5;
+constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 24 KiB
 constexpr int ACC_COLS = 256;               // TMEM columns reserved per accumulator slot
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_THREADS = 256;
-constexpr int CHUNK = 48;  // epilogue column chunk: 4 AdaGN groups of 12 channels
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_SMEM_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct KParams {
-  int M, n_out, K;
-  int rows_per_cloud, valid_rows, w_rows_per_cloud;
-  const float* bias;
-  int bias_stride;
-  int act;
-  float act_k;  // -log2(e) / (2 alpha^2)
-  const float* res;
-  long long ldr;
-  float* out_f32;
-  long long ldo32;
-  __nv_bfloat16* out_bf16;
-  long long ldo16;
-  double* stats;
-  const float* geom;
-  const float* sigma;
-  int sigma_stride;
-  float sigma_data;
-  const float* wx;
+  EpiParams e;
+  int K, w_rows_per_cloud;
   int num_m_blocks, num_n_blocks;
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-               const KParams p) {
+               const __grid_constant__ CUtensorMap tma_res, const __grid_constant__ CUtensorMap tma_o32,
+               const __grid_constant__ CUtensorMap tma_o16, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* sEpi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_SMEM_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  EpiSmem es;
+  es.res = sEpi;
+  es.o32 = sEpi + 2 * EPI_RES_BYTES;
+  es.o16 = sEpi + 4 * EPI_RES_BYTES;
+  es.res_full = bars + 2 * STAGES + 4;   // [2]
+  es.res_empty = bars + 2 * STAGES + 6;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,6 +65,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
+    if (p.e.has_res) tma_prefetch_desc(&tma_res);
+    if (p.e.has_o32) tma_prefetch_desc(&tma_o32);
+    if (p.e.has_o16) tma_prefetch_desc(&tma_o16);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -80,7 +76,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], EPI_THREADS);
+      mbar_init(&es.res_full[i], 1);
+      mbar_init(&es.res_empty[i], EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -89,6 +87,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlaps the tail of the preceding kernel (programmatic dependent launch)
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -97,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / p.num_n_blocks) * BM;
       const int n0 = (t % p.num_n_blocks) * BN;
-      const int wrow = (p.w_rows_per_cloud ? (m0 / p.rows_per_cloud) * p.w_rows_per_cloud : 0) + n0;
+      const int wrow = (p.w_rows_per_cloud ? (m0 / p.e.rows_per_cloud) * p.w_rows_per_cloud : 0) + n0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
@@ -133,130 +134,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       umma_commit(&acc_full[slot]);
     }
+  } else if (warp == 3 && lane == 0) {
+    // ------------------------------------------------------------ residual loader
+    if (p.e.has_res) {
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / p.num_n_blocks) * BM;
+        const int n0 = (t % p.num_n_blocks) * BN;
+        epi_load_residual_panel(p.e, es, &tma_res, m0, n0, cnt);
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
+    const int tid = threadIdx.x - 128;
     const int q = warp & 3;  // TMEM lane quadrant of this warp
     int it = 0;
+    uint32_t cnt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int slot = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (t / p.num_n_blocks) * BM;
       const int n0 = (t % p.num_n_blocks) * BN;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int cloud = (m0 + q * 32) / p.rows_per_cloud;  // warp-uniform (rows_per_cloud % 32 == 0)
-      const bool row_valid = row_ok && (row - cloud * p.rows_per_cloud) < p.valid_rows;
-
-      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (p.geom != nullptr && row_valid) {
-        // geom is compact [clouds, valid_rows, 3]; output rows are padded to rows_per_cloud
-        const float s = __ldg(p.sigma + (long long)cloud * p.sigma_stride);
-        const float c_in = 1.0f / sqrtf(p.sigma_data * p.sigma_data + s * s);
-        const float* gp = p.geom + ((long long)cloud * p.valid_rows + (row - cloud * p.rows_per_cloud)) * 3;
-        g0 = c_in * __ldg(gp + 0);
-        g1 = c_in * __ldg(gp + 1);
-        g2 = c_in * __ldg(gp + 2);
-      }
-
       mbar_wait(&acc_full[slot], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * ACC_COLS;
-
-#pragma unroll 1
-      for (int c = 0; c < BN / CHUNK; ++c) {
-        const int col0 = n0 + c * CHUNK;
-        if (col0 >= p.n_out) break;  // warp-uniform
-        uint32_t r[CHUNK];
-        tmem_ld16(taddr + c * CHUNK, r);
-        tmem_ld16(taddr + c * CHUNK + 16, r + 16);
-        tmem_ld16(taddr + c * CHUNK + 32, r + 32);
-        tmem_ld_wait();
-        float v[CHUNK];
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(r[j]);
-
-        if (p.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + (long long)cloud * p.bias_stride + col0);
-#pragma unroll
-          for (int j = 0; j < CHUNK / 4; ++j) {
-            if (col0 + 4 * j < p.n_out) {
-              const float4 b = __ldg(bp + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-        }
-        if (p.geom != nullptr) {
-          const float4* wp = reinterpret_cast<const float4*>(p.wx + (long long)col0 * 3);
-#pragma unroll
-          for (int j = 0; j < CHUNK / 4; ++j) {
-            if (col0 + 4 * j < p.n_out) {
-              const float4 w0 = __ldg(wp + 3 * j), w1 = __ldg(wp + 3 * j + 1), w2 = __ldg(wp + 3 * j + 2);
-              v[4 * j + 0] += g0 * w0.x + g1 * w0.y + g2 * w0.z;
-              v[4 * j + 1] += g0 * w0.w + g1 * w1.x + g2 * w1.y;
-              v[4 * j + 2] += g0 * w1.z + g1 * w1.w + g2 * w2.x;
-              v[4 * j + 3] += g0 * w2.y + g1 * w2.z + g2 * w2.w;
-            }
-          }
-        }
-        if (p.act) {
-#pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] = (exp2f(v[j] * v[j] * p.act_k) - 0.7f) * (1.0f / 0.28f);
-        }
-        if (p.res != nullptr && row_ok) {
-          const float4* rp = reinterpret_cast<const float4*>(p.res + (long long)row * p.ldr + col0);
-#pragma unroll
-          for (int j = 0; j < CHUNK / 4; ++j) {
-            if (col0 + 4 * j < p.n_out) {
-              const float4 x = rp[j];
-              v[4 * j + 0] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-            }
-          }
-        }
-        if (p.stats != nullptr) {
-          float s[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-              const float x = row_valid ? v[12 * g + j] : 0.f;
-              s1 += x;
-              s2 += x * x;
-            }
-            s[2 * g] = s1;
-            s[2 * g + 1] = s2;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] = warp_sum(s[i]);
-          float mine = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) mine = (lane == i) ? s[i] : mine;
-          if (lane < 8) {
-            // stats[cloud][col/12][{sum, sumsq}]
-            double* dst = p.stats + ((long long)cloud * (p.n_out / 12) + col0 / 12) * 2 + lane;
-            atomicAdd(dst, static_cast<double>(mine));
-          }
-        }
-        if (row_ok) {
-          if (p.out_f32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + (long long)row * p.ldo32 + col0);
-#pragma unroll
-            for (int j = 0; j < CHUNK / 4; ++j)
-              if (col0 + 4 * j < p.n_out) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out_bf16 != nullptr) {
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + (long long)row * p.ldo16 + col0);
-#pragma unroll
-            for (int j = 0; j < CHUNK / 8; ++j)
-              if (col0 + 8 * j < p.n_out)
-                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          }
-        }
-      }
+      epi_panel(p.e, es, &tma_o32, &tma_o16, taddr, m0, n0, tid, cnt);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[slot]);
     }
+    if (tid == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before_sync();
@@ -284,24 +190,48 @@ int resolve_driver() {
   return GECCO_OK;
 }
 
-// bf16 row-major [rows, cols] (ld elements) viewed as a 2D tensor {cols, rows}; box {64, box_rows}.
-int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+// Row-major [rows, cols] matrix (ld_bytes between rows) viewed as a 2D tensor {cols, rows} with a
+// {box_cols, box_rows} box.  swizzle: 128 / 64 (bytes) - the box row must span exactly that many bytes or less.
+int make_tmap(CUtensorMap* m, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_bytes,
+              uint32_t box_cols, uint32_t box_rows, int swizzle) {
   if (int rc = resolve_driver()) return rc;
   GECCO_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "operand pointer must be 16-byte aligned");
-  GECCO_REQUIRE(ld % 8 == 0, "operand leading dimension must be a multiple of 8 elements (got %llu)",
-                (unsigned long long)ld);
+  GECCO_REQUIRE(ld_bytes % 16 == 0, "operand leading dimension must be a multiple of 16 bytes (got %llu)",
+                (unsigned long long)ld_bytes);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%llu rows=%llu ld=%llu)", (int)r,
-              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%llu rows=%llu ld=%llu B box=%ux%u)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_bytes, box_cols, box_rows);
     return GECCO_ERR_CUDA;
   }
+  return GECCO_OK;
+}
+
+// bf16 MMA operand: box {64, box_rows}, SWIZZLE_128B.
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  GECCO_REQUIRE(ld % 8 == 0, "operand leading dimension must be a multiple of 8 elements (got %llu)", (unsigned long long)ld);
+  return make_tmap(m, 2, ptr, cols, rows, ld * 2, 64, box_rows, 128);
+}
+
+// Tensor maps of the epilogue (epilogue.cuh): residual / fp32 output chunks {32, 128} SWIZZLE_128B, bf16 output
+// chunks {32, 128} SWIZZLE_64B.  Unused maps are filled with a copy of `dummy`.
+int make_epilogue_tmaps(const float* res, long long ldr, float* o32, long long ldo32, void* o16, long long ldo16, int m,
+                        int n_out, const CUtensorMap& dummy, CUtensorMap* tres, CUtensorMap* t32, CUtensorMap* t16) {
+  *tres = dummy; *t32 = dummy; *t16 = dummy;
+  GECCO_REQUIRE(!res || ldr % 4 == 0, "residual leading dimension must be a multiple of 4");
+  GECCO_REQUIRE(!o32 || ldo32 % 4 == 0, "fp32 output leading dimension must be a multiple of 4");
+  GECCO_REQUIRE(!o16 || ldo16 % 8 == 0, "bf16 output leading dimension must be a multiple of 8");
+  if (res) if (int rc = make_tmap(tres, 4, res, n_out, m, ldr * 4, EPI_CHUNK, 128, 128)) return rc;
+  if (o32) if (int rc = make_tmap(t32, 4, o32, n_out, m, ldo32 * 4, EPI_CHUNK, 128, 128)) return rc;
+  if (o16) if (int rc = make_tmap(t16, 2, o16, n_out, m, ldo16 * 2, EPI_CHUNK, 128, 64)) return rc;
   return GECCO_OK;
 }
 
@@ -313,31 +243,28 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
                 a.rows_per_cloud);
   GECCO_REQUIRE(a.valid_rows > 0 && a.valid_rows <= a.rows_per_cloud, "gemm: valid_rows out of range");
   GECCO_REQUIRE(a.out_f32 || a.out_bf16, "gemm: no output buffer");
-  GECCO_REQUIRE(!a.stats || a.n_out % 48 == 0, "gemm: statistics epilogue needs n_out %% 48 == 0");
+  GECCO_REQUIRE(!a.stats || a.n_out % 12 == 0, "gemm: statistics epilogue needs n_out %% 12 == 0");
   GECCO_REQUIRE(!a.geom || (a.sigma && a.wx), "gemm: xyz embed needs sigma and wx");
   GECCO_REQUIRE(!a.w_rows_per_cloud || a.rows_per_cloud % BM == 0,
                 "gemm: per-cloud weights need rows_per_cloud %% 128 == 0");
-  GECCO_REQUIRE(!a.res || a.ldr % 4 == 0, "gemm: residual leading dimension must be a multiple of 4");
-  GECCO_REQUIRE(!a.out_f32 || a.ldo32 % 4 == 0, "gemm: fp32 output leading dimension must be a multiple of 4");
-  GECCO_REQUIRE(!a.out_bf16 || a.ldo16 % 8 == 0, "gemm: bf16 output leading dimension must be a multiple of 8");
 
   const int clouds = ceil_div(a.m, a.rows_per_cloud);
-  const uint64_t w_rows = a.w_rows_per_cloud ? (uint64_t)a.w_rows_per_cloud * clouds : (uint64_t)a.n_out;
-  CUtensorMap ta, tw;
+  const uint64_t w_rows = a.w_rows_per_cloud ? (uint64_t)a.w_rows_per_cloud * (clouds - 1) + a.n_out : (uint64_t)a.n_out;
+  CUtensorMap ta, tw, tres, t32, t16;
   if (int rc = make_tmap_bf16(&ta, a.a, a.k, a.m, a.lda, BM)) return rc;
   if (int rc = make_tmap_bf16(&tw, a.w, a.k, w_rows, a.ldw, BN)) return rc;
+  if (int rc = make_epilogue_tmaps(a.res, a.ldr, a.out_f32, a.ldo32, a.out_bf16, a.ldo16, a.m, a.n_out, ta, &tres, &t32, &t16))
+    return rc;
 
   KParams p;
-  p.M = a.m; p.n_out = a.n_out; p.K = a.k;
-  p.rows_per_cloud = a.rows_per_cloud; p.valid_rows = a.valid_rows; p.w_rows_per_cloud = a.w_rows_per_cloud;
-  p.bias = a.bias; p.bias_stride = a.bias_stride;
-  p.act = a.act;
-  p.act_k = a.act ? static_cast<float>(-1.4426950408889634 / (2.0 * (double)a.act_alpha * (double)a.act_alpha)) : 0.f;
-  p.res = a.res; p.ldr = a.ldr;
-  p.out_f32 = a.out_f32; p.ldo32 = a.ldo32;
-  p.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16); p.ldo16 = a.ldo16;
-  p.stats = a.stats;
-  p.geom = a.geom; p.sigma = a.sigma; p.sigma_stride = a.sigma_stride; p.sigma_data = a.sigma_data; p.wx = a.wx;
+  p.e.M = a.m; p.e.n_out = a.n_out; p.K = a.k;
+  p.e.rows_per_cloud = a.rows_per_cloud; p.e.valid_rows = a.valid_rows; p.w_rows_per_cloud = a.w_rows_per_cloud;
+  p.e.bias = a.bias; p.e.bias_stride = a.bias_stride;
+  p.e.act = a.act;
+  p.e.act_k = a.act ? static_cast<float>(-1.4426950408889634 / (2.0 * (double)a.act_alpha * (double)a.act_alpha)) : 0.f;
+  p.e.has_res = a.res != nullptr; p.e.has_o32 = a.out_f32 != nullptr; p.e.has_o16 = a.out_bf16 != nullptr;
+  p.e.stats = a.stats;
+  p.e.geom = a.geom; p.e.sigma = a.sigma; p.e.sigma_stride = a.sigma_stride; p.e.sigma_data = a.sigma_data; p.e.wx = a.wx;
   p.num_m_blocks = ceil_div(a.m, BM);
   p.num_n_blocks = ceil_div(a.n_out, BN);
 
@@ -349,7 +276,18 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tw, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, ta, tw, tres, t32, t16, p);
+  if (le != cudaSuccess) return fail_cuda(le, "gemm_tc_kernel launch");
   GECCO_CHECK_LAUNCH("gemm_tc_kernel launch");
   return GECCO_OK;
 }

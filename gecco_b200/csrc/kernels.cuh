@@ -8,6 +8,7 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t s);
 int launch_group_stats(const float* x, long long ldx, int clouds, int rows_per_cloud, int valid_rows, int C, int gs,
                        double* stats, cudaStream_t s);
 int launch_adagn(const gecco_adagn_args& a, cudaStream_t s);
+int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s);
 int launch_lift(const gecco_lift_args& a, cudaStream_t s);
 int launch_head(const gecco_head_args& a, cudaStream_t s);
 int launch_sampler_init(const float* latents, const float* noise, double t0, double churn, long long n, double* x_hat,

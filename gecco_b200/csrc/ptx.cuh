@@ -69,6 +69,32 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// 2D tiled store shared -> global (bulk async group of the issuing thread); out-of-bounds elements are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Waits until at most N of this thread's bulk groups still READ their shared-memory source.
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// Sub-block barrier over `threads` threads (id 1..15; id 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// Byte offset of logical offset `off` inside a 1024 B-aligned tile written / read by TMA with
+// SWIZZLE_128B (16 B chunk index bits [4,7) xor row bits [7,10)) or SWIZZLE_64B (bits [4,6) xor [7,9)).
+__device__ __forceinline__ uint32_t swz128(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
+__device__ __forceinline__ uint32_t swz64(uint32_t off) { return off ^ (((off >> 7) & 3u) << 4); }
+
+// Programmatic dependent launch: wait for the preceding grid's memory / let the next grid start its prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {

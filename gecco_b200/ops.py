@@ -149,8 +149,31 @@ def adagn(x: Tensor, stats: Tensor, stat_gs: int, t: Tensor, scale_w: Tensor, sc
     return out_f32, out_bf16
 
 
+def fold_adagn(w: Tensor, bias: Tensor | None, stats: Tensor, t: Tensor, scale_w: Tensor, scale_b: Tensor, bias_w: Tensor,
+               bias_b: Tensor, *, clouds: int, valid_rows: int, groups: int = 32, stat_gs: int = STAT_GS, eps: float = 1e-5):
+    """AdaGN + Linear folded per cloud: returns (w_folded bf16 [clouds, n_out, C], bias_folded fp32 [clouds, n_out])."""
+    lib = _lib_for(w)
+    assert w.dtype == torch.float32 and w.stride(1) == 1 and stats.dtype == torch.float64
+    n_out, c = w.shape
+    wf = torch.empty((clouds, n_out, c), device=w.device, dtype=torch.bfloat16)
+    bf = torch.empty((clouds, n_out), device=w.device, dtype=torch.float32)
+    a = _abi.FoldAdaGNArgs()
+    a.w, a.ldw = w.data_ptr(), w.stride(0)
+    a.bias = 0 if bias is None else bias.data_ptr()
+    a.n_out, a.c = n_out, c
+    a.stats, a.stat_gs, a.groups, a.valid_rows, a.eps = stats.data_ptr(), stat_gs, groups, valid_rows, eps
+    a.t, a.t_stride, a.ctx_dim = t.data_ptr(), 1, 1
+    a.scale_w, a.scale_b, a.bias_w, a.bias_b = scale_w.data_ptr(), scale_b.data_ptr(), bias_w.data_ptr(), bias_b.data_ptr()
+    a.clouds = clouds
+    a.w_folded_bf16, a.ldwf, a.wf_cloud_stride = wf.data_ptr(), c, n_out * c
+    a.bias_folded, a.bias_stride = bf.data_ptr(), n_out
+    _abi.check(lib.gecco_fold_adagn(C.byref(a), _stream(w)))
+    return wf, bf
+
+
 def lift(xin: Tensor, w: Tensor, b: Tensor, *, rows_per_cloud: int, sigma: Tensor | None = None, sigma_stride: int = 1,
-         sigma_data: float = 1.0, stats: Tensor | None = None, stat_gs: int = STAT_GS, out: Tensor | None = None) -> Tensor:
+         sigma_data: float = 1.0, stats: Tensor | None = None, stat_gs: int = STAT_GS, out: Tensor | None = None,
+         out_bf16: Tensor | None = None) -> Tensor:
     lib = _lib_for(xin)
     assert xin.dtype == torch.float32 and xin.is_contiguous() and xin.shape[-1] == 3
     clouds, n = xin.shape[0], xin.shape[1]
@@ -163,6 +186,8 @@ def lift(xin: Tensor, w: Tensor, b: Tensor, *, rows_per_cloud: int, sigma: Tenso
     a.w, a.b = w.data_ptr(), b.data_ptr()
     a.clouds, a.rows_per_cloud, a.valid_rows, a.c = clouds, rows_per_cloud, n, c
     a.x, a.ldx = out.data_ptr(), out.stride(0)
+    if out_bf16 is not None:
+        a.x_bf16, a.ldxb = out_bf16.data_ptr(), out_bf16.stride(0)
     a.stats, a.stat_gs = (0 if stats is None else stats.data_ptr()), stat_gs
     _abi.check(lib.gecco_lift(C.byref(a), _stream(xin)))
     return out

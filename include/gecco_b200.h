@@ -102,6 +102,24 @@ typedef struct gecco_adagn_args {
 } gecco_adagn_args;
 int gecco_adagn(const gecco_adagn_args* args, void* stream);
 
+/* AdaGN (models/normalization.py:36-44) followed by an nn.Linear, folded into per-cloud weights so that the
+ * projection reads the un-normalised bf16 residual stream:
+ *   w_folded[cloud][o][c] = w[o][c] * a[cloud][c],  bias_folded[cloud][o] = bias[o] + sum_c w[o][c] * s[cloud][c]
+ *   a = scale(t) * rstd_g,  s = bias(t) - a * mean_g   (mean / rstd from stats over valid_rows * C/groups elements).
+ * Used for kv_proj + the unpool q projection (set_transformer.py:49,112) and mlp.0 (mlp.py:5-39). */
+typedef struct gecco_fold_adagn_args {
+  const float* w; int64_t ldw;      /* fp32 [n_out, C] */
+  const float* bias;                /* [n_out] or NULL */
+  int32_t n_out, c;
+  const double* stats; int32_t stat_gs; int32_t groups; int32_t valid_rows; float eps;
+  const float* t; int32_t t_stride; int32_t ctx_dim;
+  const float* scale_w; const float* scale_b; const float* bias_w; const float* bias_b;
+  int32_t clouds;
+  void* w_folded_bf16; int64_t ldwf; int64_t wf_cloud_stride;   /* elements */
+  float* bias_folded; int32_t bias_stride;
+} gecco_fold_adagn_args;
+int gecco_fold_adagn(const gecco_fold_adagn_args* args, void* stream);
+
 /* LinearLift.lift (models/linear_lift.py:21,44) on the EDM-scaled input:
  *   x[b,n,:] = W (c_in(sigma_b) * xin[b,n,:]) + bias, c_in = 1/sqrt(sigma_data^2 + sigma^2)
  * (sigma NULL: c_in = 1) and, when stats != NULL, the statistics of x for the first AdaGN. */
@@ -111,6 +129,7 @@ typedef struct gecco_lift_args {
   const float* w; const float* b;   /* [C, 3], [C] */
   int32_t clouds, rows_per_cloud, valid_rows, c;
   float* x; int64_t ldx;            /* [clouds*rows_per_cloud, C] */
+  void* x_bf16; int64_t ldxb;       /* optional bf16 copy of x (the operand of the first projections) */
   double* stats; int32_t stat_gs;
 } gecco_lift_args;
 int gecco_lift(const gecco_lift_args* args, void* stream);
