@@ -4,20 +4,22 @@
 // All global traffic of the epilogue goes through TMA: the residual chunk is prefetched into swizzled shared
 // memory by a loader thread (res_full / res_empty mbarriers), results are staged in swizzled shared memory and
 // written with bulk tensor stores, so every global access is a full 128 B (fp32) / 64 B (bf16) row segment
-// regardless of the one-thread-per-row TMEM layout.  128 epilogue threads (4 warps, warp q <-> TMEM lanes 32q..).
+// regardless of the one-thread-per-row TMEM layout.  Two epilogue groups of 128 threads (4 warps each, warp q <->
+// TMEM lanes 32q..) work on alternate chunks with their own staging buffers, barriers and bulk-store thread.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace gecco {
 
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 128;                      // per group
+constexpr int EPI_GROUPS = 2;
 constexpr int EPI_CHUNK = 32;                         // columns per chunk
 constexpr int EPI_PANEL = 192;                        // columns per panel (16 AdaGN groups of 12)
 constexpr int EPI_RES_BYTES = 128 * EPI_CHUNK * 4;    // one fp32 chunk (TMA box {32, 128}, SWIZZLE_128B)
 constexpr int EPI_O16_BYTES = 128 * EPI_CHUNK * 2;    // one bf16 chunk (TMA box {32, 128}, SWIZZLE_64B)
 constexpr int EPI_SMEM_BYTES = 4 * EPI_RES_BYTES + 2 * EPI_O16_BYTES;  // res[2] | o32[2] | o16[2]
-constexpr int EPI_BAR_STAGE = 1, EPI_BAR_FREE = 2;    // named barrier ids
+constexpr int EPI_BAR_STAGE = 1, EPI_BAR_FREE = 2;    // named barrier ids (+ 2 * group)
 
 struct EpiParams {
   int M, n_out;
@@ -36,25 +38,25 @@ struct EpiParams {
 };
 
 struct EpiSmem {
-  uint8_t* res;  // 2 x EPI_RES_BYTES, 1024 B aligned
-  uint8_t* o32;  // 2 x EPI_RES_BYTES
-  uint8_t* o16;  // 2 x EPI_O16_BYTES
-  uint64_t* res_full;   // [2], count 1 + tx
-  uint64_t* res_empty;  // [2], count EPI_THREADS
+  uint8_t* res;  // [group] x EPI_RES_BYTES, 1024 B aligned
+  uint8_t* o32;  // [group] x EPI_RES_BYTES
+  uint8_t* o16;  // [group] x EPI_O16_BYTES
+  uint64_t* res_full;   // [group], count 1 + tx
+  uint64_t* res_empty;  // [group], count EPI_THREADS
 };
 
 // Loader side (one thread): prefetches the residual chunks of one panel in the order the epilogue consumes them.
 __device__ __forceinline__ void epi_load_residual_panel(const EpiParams& p, const EpiSmem& sm, const CUtensorMap* tma_res,
-                                                        int m0, int n0, uint32_t& cnt) {
+                                                        int m0, int n0, uint32_t (&cnt)[EPI_GROUPS]) {
 #pragma unroll 1
   for (int c = 0; c < EPI_PANEL / EPI_CHUNK; ++c) {
     const int col0 = n0 + c * EPI_CHUNK;
     if (col0 >= p.n_out) break;
-    const uint32_t buf = cnt & 1u, phase = (cnt >> 1) & 1u;
+    const uint32_t buf = c & 1u, phase = cnt[buf] & 1u;  // chunk c belongs to group c & 1
     mbar_wait(&sm.res_empty[buf], phase ^ 1u);
     mbar_arrive_expect_tx(&sm.res_full[buf], EPI_RES_BYTES);
     tma_load_2d(sm.res + buf * EPI_RES_BYTES, tma_res, &sm.res_full[buf], col0, m0);
-    ++cnt;
+    ++cnt[buf];
   }
 }
 
@@ -73,10 +75,11 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
   return v[0];
 }
 
-// Epilogue side (all EPI_THREADS threads).  taddr: TMEM address of (lane quadrant q, panel column 0).
-// tid: 0..127 within the epilogue group; `cnt` counts chunks processed by this CTA (same sequence as the loader).
+// Epilogue side (all threads of both groups).  taddr: TMEM address of (lane quadrant q, panel column 0).
+// grp: epilogue group of this thread, tid: 0..127 within the group; `cnt` counts the chunks this group has processed
+// (the loader keeps the same count per group).
 __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm, const CUtensorMap* tma_o32,
-                                          const CUtensorMap* tma_o16, uint32_t taddr, int m0, int n0, int tid,
+                                          const CUtensorMap* tma_o16, uint32_t taddr, int m0, int n0, int grp, int tid,
                                           uint32_t& cnt) {
   const int q = tid >> 5, lane = tid & 31;
   const int r = q * 32 + lane;  // row inside the tile == TMEM lane
@@ -101,7 +104,7 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
 #pragma unroll
   for (int c = 0; c < EPI_PANEL / EPI_CHUNK; ++c) {
     const int col0 = n0 + c * EPI_CHUNK;
-    if (col0 < p.n_out) {  // uniform over the epilogue group
+    if ((c & 1) == grp && col0 < p.n_out) {  // uniform over the epilogue group
       uint32_t rr[EPI_CHUNK];
       tmem_ld16(taddr + c * EPI_CHUNK, rr);
       tmem_ld16(taddr + c * EPI_CHUNK + 16, rr + 16);
@@ -137,7 +140,7 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
 #pragma unroll
         for (int j = 0; j < EPI_CHUNK; ++j) v[j] = (exp2f(v[j] * v[j] * p.act_k) - 0.7f) * (1.0f / 0.28f);
       }
-      const uint32_t buf = cnt & 1u, phase = (cnt >> 1) & 1u;
+      const uint32_t buf = grp, phase = cnt & 1u;
       if (p.has_res) {
         mbar_wait(&sm.res_full[buf], phase);
         const uint8_t* rb = sm.res + buf * EPI_RES_BYTES;
@@ -160,9 +163,9 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
           st[2 * g + 1] += v[j] * v[j];
         }
       }
-      // staging buffer `buf` was last read by the bulk store of chunk cnt-2
-      if (tid == 0) tma_store_wait_read<1>();
-      named_bar_sync(EPI_BAR_FREE, EPI_THREADS);
+      // the staging buffers of this group were last read by the bulk store of its previous chunk
+      if (tid == 0) tma_store_wait_read<0>();
+      named_bar_sync(EPI_BAR_FREE + 2 * grp, EPI_THREADS);
       if (p.has_o32) {
         uint8_t* ob = sm.o32 + buf * EPI_RES_BYTES;
 #pragma unroll
@@ -178,7 +181,7 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
       }
       fence_proxy_async_smem();
-      named_bar_sync(EPI_BAR_STAGE, EPI_THREADS);
+      named_bar_sync(EPI_BAR_STAGE + 2 * grp, EPI_THREADS);
       if (tid == 0) {
         if (p.has_o32) tma_store_2d(tma_o32, sm.o32 + buf * EPI_RES_BYTES, col0, m0);
         if (p.has_o16) tma_store_2d(tma_o16, sm.o16 + buf * EPI_O16_BYTES, col0, m0);

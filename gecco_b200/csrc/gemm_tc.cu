@@ -4,8 +4,9 @@
 //   warp 1 : MMA issuer    (one thread; 4 x tcgen05.mma M=128 N=192 K=16 per stage)
 //   warp 2 : TMEM allocator (512 columns = two 192-wide fp32 accumulator slots)
 //   warp 3 : residual loader (TMA prefetch of the fp32 residual chunks the epilogue will add)
-//   warps 4-7 : epilogue   (epilogue.cuh: tcgen05.ld -> bias / xyz-embed / activation / residual /
-//                           AdaGN statistics -> swizzled smem staging -> TMA bulk stores, fp32 and/or bf16)
+//   warps 4-11 : epilogue  (epilogue.cuh: tcgen05.ld -> bias / xyz-embed / activation / residual /
+//                           AdaGN statistics -> swizzled smem staging -> TMA bulk stores, fp32 and/or bf16;
+//                           two groups of 4 warps on alternate 32-column chunks)
 // The two TMEM slots let the epilogue of tile i overlap the main loop of tile i+1.
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -26,7 +27,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 24 KiB
 constexpr int ACC_COLS = 256;               // TMEM columns reserved per accumulator slot
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 128 + EPI_GROUPS * EPI_THREADS;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_SMEM_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct KParams {
@@ -51,8 +52,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
   EpiSmem es;
   es.res = sEpi;
-  es.o32 = sEpi + 2 * EPI_RES_BYTES;
-  es.o16 = sEpi + 4 * EPI_RES_BYTES;
+  es.o32 = sEpi + EPI_GROUPS * EPI_RES_BYTES;
+  es.o16 = sEpi + 2 * EPI_GROUPS * EPI_RES_BYTES;
   es.res_full = bars + 2 * STAGES + 4;   // [2]
   es.res_empty = bars + 2 * STAGES + 6;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
@@ -76,7 +77,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_THREADS);
+      mbar_init(&acc_empty[i], EPI_GROUPS * EPI_THREADS);
       mbar_init(&es.res_full[i], 1);
       mbar_init(&es.res_empty[i], EPI_THREADS);
     }
@@ -137,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == 3 && lane == 0) {
     // ------------------------------------------------------------ residual loader
     if (p.e.has_res) {
-      uint32_t cnt = 0;
+      uint32_t cnt[EPI_GROUPS] = {0, 0};
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / p.num_n_blocks) * BM;
         const int n0 = (t % p.num_n_blocks) * BN;
@@ -146,7 +147,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    const int tid = threadIdx.x - 128;
+    const int grp = (warp - 4) >> 2;
+    const int tid = threadIdx.x & (EPI_THREADS - 1);
     const int q = warp & 3;  // TMEM lane quadrant of this warp
     int it = 0;
     uint32_t cnt = 0;
@@ -158,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(&acc_full[slot], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * ACC_COLS;
-      epi_panel(p.e, es, &tma_o32, &tma_o16, taddr, m0, n0, tid, cnt);
+      epi_panel(p.e, es, &tma_o32, &tma_o16, taddr, m0, n0, grp, tid, cnt);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[slot]);
     }

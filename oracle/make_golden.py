@@ -136,13 +136,15 @@ def main():
         c_in = 1 / (1 + sig**2).sqrt()
         look = model.backbone.model.extract_image_features(x * c_in[:, None, None], feats, ctx)
         samp = model.sample_stochastic((2, 200, 3), ctx, rng=synth.gen(43), num_steps=5)
+        samp2 = model.sample_stochastic((2, 160, 3), ctx, rng=synth.gen(5), num_steps=2)  # short trajectory
     drift = dict(D=rel_rms(bf16_drift(lambda: model(x, sig, ctx)).float(), D),
-                 sample=rel_rms(bf16_drift(lambda: model.sample_stochastic((2, 200, 3), ctx, rng=synth.gen(43), num_steps=5)), samp))
+                 sample=rel_rms(bf16_drift(lambda: model.sample_stochastic((2, 200, 3), ctx, rng=synth.gen(43), num_steps=5)), samp),
+                 sample2=rel_rms(bf16_drift(lambda: model.sample_stochastic((2, 160, 3), ctx, rng=synth.gen(5), num_steps=2)), samp2))
     print("cond_gaussian bf16-autocast drift of the reference", drift)
     torch.save(dict(drift=drift, recipe={**recipe_common, **cfg, "K": synth.K_SHAPENET, "feat_sizes": (34, 17, 8), "feat_seed": 21,
                             "x_seed": 22, "x_scale": 2.0, "B": B, "N": N, "noise_sigma": sig,
                             "sample_shape": (2, 200, 3), "sample_seed": 43, "sample_steps": 5},
-                    D=D, lookup_sub=look[:, ::3].contiguous(), sample=samp),
+                    D=D, lookup_sub=look[:, ::3].contiguous(), sample=samp, sample2=samp2),
                OUT / "cond_gaussian.pt")
     print("cond_gaussian", D.abs().mean().item(), look.abs().mean().item(), samp.abs().mean().item())
 
@@ -163,6 +165,8 @@ def main():
         x2 = torch.randn(B, 500, 3, generator=synth.gen(33)) * 1.5
         D_cached = model(x2, sig, ctx, cache=hs)
         samp = model.sample_stochastic((2, 192, 3), ctx, rng=synth.gen(44), num_steps=5)
+        # short trajectory (sigma_max lowered so that exp() of the ray-length coordinate stays finite after one giant step)
+        samp2 = model.sample_stochastic((2, 160, 3), ctx, rng=synth.gen(5), num_steps=2, sigma_max=2.0)
         # reparam round trip on in-frustum data
         diff = torch.randn(B, 64, 3, generator=synth.gen(34))
         data = model.reparam.diffusion_to_data(diff, ctx)
@@ -174,6 +178,8 @@ def main():
     drift = dict(D=rel_rms(bf16_drift(lambda: model(x, sig, ctx)).float(), D),
                  sample=rel_rms(to_diff(bf16_drift(lambda: model.sample_stochastic((2, 192, 3), ctx, rng=synth.gen(44), num_steps=5))),
                                 to_diff(samp)),
+                 sample2=rel_rms(to_diff(bf16_drift(lambda: model.sample_stochastic((2, 160, 3), ctx, rng=synth.gen(5), num_steps=2,
+                                                                                     sigma_max=2.0))), to_diff(samp2)),
                  upsample=rel_rms(to_diff(bf16_drift(lambda: model.upsample(seed_cloud, n_new=384, context=ctx, seed=7,
                                                                               num_substeps=2, num_steps=3))), to_diff(ups)))
     print("cond_uvl bf16-autocast drift of the reference (samples in diffusion space)", drift)
@@ -183,7 +189,7 @@ def main():
                             "rt_seed": 34, "ups_seed_cloud_seed": 35, "ups_n_seed": 128, "ups_n_new": 384,
                             "ups_seed": 7, "ups_substeps": 2, "ups_steps": 3},
                     D=D, hs_sub=[sub(h) for h in hs], lookup_sub=look[:, ::3].contiguous(), D_cached=D_cached,
-                    sample=samp, rt_data=data, rt_back=back, upsample=ups),
+                    sample=samp, sample2=samp2, rt_data=data, rt_back=back, upsample=ups),
                OUT / "cond_uvl.pt")
     print("cond_uvl", D.abs().mean().item(), look.abs().mean().item(), samp.abs().mean().item(), ups.abs().mean().item(),
           (back - diff).abs().max().item())

@@ -8,7 +8,8 @@ reference's own bf16-autocast drift at rms 3.9e-3 * rms(F), max 1.7e-2):
   sampled points:         rms error <= max(2e-2, the reference's own bf16-autocast drift on the same call) * rms(sample).
 The multi-step sampler amplifies any perturbation (with the randomised synthetic weights the conditional sampler is
 chaotic: the UNMODIFIED reference drifts by 9e-2 .. 3.6e-1 under its own bf16 autocast), so the golden files carry that
-drift (`drift`, measured by oracle/make_golden.py) and 2-step sampler runs are additionally checked against the oracle.
+drift (`drift`, measured by oracle/make_golden.py).  2-step sampler runs are additionally checked against the oracle and
+the reference golden with tolerance max(2e-2, half the reference's own bf16 drift on that call).
 """
 from pathlib import Path
 
@@ -100,8 +101,10 @@ def test_cond_gaussian(cuda):
     s2 = model.sample_stochastic((2, 160, 3), ctx, rng=synth.gen(5), num_steps=2)
     o2 = O.sample_stochastic(cfg, sd, (2, 160, 3), feats, synth.camera(r["B"], r["K"]), rng=synth.gen(5), num_steps=2)
     e = rms(s2.cpu() - o2) / rms(o2)
-    print("cond_gaussian 2-step sample rel rms", e)
-    assert e < 2e-2
+    eg = rms(s2.cpu() - g["sample2"]) / rms(g["sample2"])
+    tol = max(2e-2, 0.5 * g["drift"]["sample2"])  # at least twice as close as the reference's own bf16 autocast
+    print("cond_gaussian 2-step sample rel rms vs oracle", e, "vs reference golden", eg, "tolerance", tol)
+    assert e < tol and eg < tol
 
 
 def test_cond_uvl(cuda):
@@ -142,8 +145,10 @@ def test_cond_uvl(cuda):
     o2 = O.sample_stochastic(cfg, sdf, (2, 160, 3), feats, K, rng=synth.gen(5), num_steps=2, sigma_max=2.0)
     assert torch.isfinite(o2).all() and torch.isfinite(s2).all()
     e = rms(to_diff(s2) - to_diff(o2)) / rms(to_diff(o2))
-    print("cond_uvl 2-step sample rel rms", e)
-    assert e < 2e-2
+    eg = rms(to_diff(s2) - to_diff(g["sample2"])) / rms(to_diff(g["sample2"]))
+    tol = max(2e-2, 0.5 * g["drift"]["sample2"])  # at least twice as close as the reference's own bf16 autocast
+    print("cond_uvl 2-step sample rel rms vs oracle", e, "vs reference golden", eg, "tolerance", tol)
+    assert e < tol and eg < tol
     seed_cloud = O.diffusion_to_data(cfg, sd, torch.randn(r["B"], r["ups_n_seed"], 3, generator=synth.gen(r["ups_seed_cloud_seed"])), K)
     u = model.upsample(seed_cloud.to(cuda), n_new=r["ups_n_new"], context=ctx, num_substeps=r["ups_substeps"],
                        num_steps=r["ups_steps"], rng=synth.gen(r["ups_seed"]))
