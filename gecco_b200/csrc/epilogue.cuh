@@ -1,14 +1,17 @@
 // Row-tile epilogue shared by the tcgen05 kernels: drains a 128-row x 192-column fp32 accumulator panel from
 // TMEM in 32-column chunks and applies, in this order,
 //   + bias[cloud][n]  + xyz embed  -> Gaussian activation -> + residual -> AdaGN statistics -> fp32 / bf16 stores.
-// All global traffic of the epilogue goes through TMA: the residual chunk is prefetched into swizzled shared
-// memory by a loader thread (res_full / res_empty mbarriers), results are staged in swizzled shared memory and
-// written with bulk tensor stores, so every global access is a full 128 B (fp32) / 64 B (bf16) row segment
-// regardless of the one-thread-per-row TMEM layout.  Two epilogue groups of 128 threads (4 warps each, warp q <->
-// TMEM lanes 32q..) work on alternate chunks with their own staging buffers, barriers and bulk-store thread.
+// The TMEM layout gives every thread one ROW of the tile; global memory wants whole rows segments per warp
+// instruction.  Inputs: the fp32 residual chunk is prefetched by TMA into swizzled shared memory by a loader thread
+// (res_full / res_empty mbarriers, one buffer per group).  Outputs: every warp transposes its own 32 x 32 chunk
+// through a private swizzled staging area (only __syncwarp, no block barrier, no bulk-store latency) and writes it
+// with coalesced 16 B stores: 4 rows x 128 B (fp32) or 8 rows x 64 B (bf16) per instruction, full sectors only.
+// Two epilogue groups of 128 threads (4 warps each, warp q <-> TMEM lanes 32q..) work on alternate chunks.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+
+#include <type_traits>
 
 namespace gecco {
 
@@ -18,8 +21,8 @@ constexpr int EPI_CHUNK = 32;                         // columns per chunk
 constexpr int EPI_PANEL = 192;                        // columns per panel (16 AdaGN groups of 12)
 constexpr int EPI_RES_BYTES = 128 * EPI_CHUNK * 4;    // one fp32 chunk (TMA box {32, 128}, SWIZZLE_128B)
 constexpr int EPI_O16_BYTES = 128 * EPI_CHUNK * 2;    // one bf16 chunk (TMA box {32, 128}, SWIZZLE_64B)
-constexpr int EPI_SMEM_BYTES = 4 * EPI_RES_BYTES + 2 * EPI_O16_BYTES;  // res[2] | o32[2] | o16[2]
-constexpr int EPI_BAR_STAGE = 1, EPI_BAR_FREE = 2;    // named barrier ids (+ 2 * group)
+constexpr int EPI_BIAS_BYTES = 8 * 384;                // per-warp bias staging (3 chunks x 32 floats)
+constexpr int EPI_SMEM_BYTES = 4 * EPI_RES_BYTES + 2 * EPI_O16_BYTES + EPI_BIAS_BYTES;  // res[2] | o32 | o16 | bias
 
 struct EpiParams {
   int M, n_out;
@@ -28,7 +31,9 @@ struct EpiParams {
   int bias_stride;
   int act;
   float act_k;  // -log2(e) / (2 alpha^2)
-  int has_res, has_o32, has_o16;
+  int has_res;
+  float* o32;           // fp32 output or nullptr (written through its tensor map)
+  __nv_bfloat16* o16;   // bf16 output or nullptr
   double* stats;  // [clouds][n_out / 12][2] or nullptr
   const float* geom;  // [clouds, valid_rows, 3] or nullptr
   const float* sigma;
@@ -39,11 +44,29 @@ struct EpiParams {
 
 struct EpiSmem {
   uint8_t* res;  // [group] x EPI_RES_BYTES, 1024 B aligned
-  uint8_t* o32;  // [group] x EPI_RES_BYTES
-  uint8_t* o16;  // [group] x EPI_O16_BYTES
+  uint8_t* o32;  // [group][warp] x 4 KB fp32 staging (32 rows x 128 B, 128 B swizzle)
+  uint8_t* o16;  // [group][warp] x 2 KB bf16 staging (32 rows x 64 B, 64 B swizzle)
+  uint8_t* bias; // [group][warp] x 384 B
   uint64_t* res_full;   // [group], count 1 + tx
   uint64_t* res_empty;  // [group], count EPI_THREADS
 };
+
+// Shared memory the epilogue needs for a given output configuration (1024 B aligned pieces), and its carving.
+__host__ __device__ inline int epi_smem_bytes(bool has_res, bool has_o32, bool has_o16) {
+  return (has_res ? EPI_GROUPS * EPI_RES_BYTES : 0) + (has_o32 ? EPI_GROUPS * EPI_RES_BYTES : 0) +
+         (has_o16 ? EPI_GROUPS * EPI_O16_BYTES : 0) + EPI_BIAS_BYTES;
+}
+// Returns the first byte after the epilogue's area.
+__device__ __forceinline__ uint8_t* epi_smem_carve(EpiSmem& es, uint8_t* base, bool has_res, bool has_o32, bool has_o16) {
+  es.res = base;
+  if (has_res) base += EPI_GROUPS * EPI_RES_BYTES;
+  es.o32 = base;
+  if (has_o32) base += EPI_GROUPS * EPI_RES_BYTES;
+  es.o16 = base;
+  if (has_o16) base += EPI_GROUPS * EPI_O16_BYTES;
+  es.bias = base;
+  return base + EPI_BIAS_BYTES;
+}
 
 // Loader side (one thread): prefetches the residual chunks of one panel in the order the epilogue consumes them.
 __device__ __forceinline__ void epi_load_residual_panel(const EpiParams& p, const EpiSmem& sm, const CUtensorMap* tma_res,
@@ -75,125 +98,236 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
   return v[0];
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr)
+      : "memory");
+}
+// tcgen05.wait::ld with the loaded registers as operands, so that no use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// Per-thread constants of the epilogue (shared-window addresses of the staging areas), computed once per kernel.
+struct EpiThread {
+  int grp, q, lane;
+  uint32_t x7;          // (lane & 7) << 4: 128 B swizzle term of row `lane` (and of tile row q*32+lane)
+  uint32_t w32;         // fp32 staging, write side: piece j of row `lane` at  w32 | ((j << 4) ^ x7)
+  uint32_t r32e, r32o;  // fp32 staging, read side: rows 4i + lane/8, piece lane%8: (i even ? r32e : r32o) + i * 512
+  uint32_t x3, w16;     // bf16 staging, write side: piece j of row `lane` at  w16 | ((j << 4) ^ x3)
+  uint32_t r16;         // bf16 staging, read side: rows 8i + lane/4, piece lane%4: r16 + i * 512
+  uint32_t s32, s16;    // bases of this warp's staging areas (sources of the bulk stores)
+  uint32_t res;         // residual chunk of this group, row q*32+lane: piece j at  res | ((j << 4) ^ x7)
+  uint32_t bias;        // per-warp bias staging: 3 chunks x 32 floats
+};
+
+__device__ __forceinline__ EpiThread epi_thread_init(const EpiSmem& sm, int grp, int tid) {
+  EpiThread t;
+  t.grp = grp; t.q = tid >> 5; t.lane = tid & 31;
+  const uint32_t lane = t.lane, w = grp * 4 + t.q;
+  t.x7 = (lane & 7u) << 4;
+  const uint32_t s32 = smem_u32(sm.o32) + w * 4096u;
+  t.w32 = s32 + lane * 128u;
+  t.s32 = s32;
+  const uint32_t rr = lane >> 3, jj = lane & 7u;
+  t.r32e = s32 + rr * 128u + ((jj ^ rr) << 4);
+  t.r32o = s32 + rr * 128u + ((jj ^ (rr + 4u)) << 4);
+  t.x3 = ((lane >> 1) & 3u) << 4;
+  const uint32_t s16 = smem_u32(sm.o16) + w * 2048u;
+  t.w16 = s16 + lane * 64u;
+  t.s16 = s16;
+  t.r16 = s16 + (lane >> 2) * 64u + (((lane & 3u) ^ ((lane >> 3) & 3u)) << 4);
+  t.res = smem_u32(sm.res) + grp * EPI_RES_BYTES + (t.q * 32u + lane) * 128u;
+  t.bias = smem_u32(sm.bias) + w * 384u;
+  return t;
+}
+
+// Before the accumulator is waited for: stage the bias of this group's three chunks (latency overlaps the wait).
+__device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiThread& t, int m0, int n0) {
+  if (p.bias == nullptr) return;
+  const int cloud = (m0 + t.q * 32) / p.rows_per_cloud;
+  const float* bp = p.bias + (long long)cloud * p.bias_stride + n0 + t.grp * EPI_CHUNK + t.lane;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int col = n0 + (2 * k + t.grp) * EPI_CHUNK + t.lane;
+    const float b = col < p.n_out ? __ldg(bp + 2 * k * EPI_CHUNK) : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(t.bias + k * 128u + t.lane * 4u), "f"(b) : "memory");
+  }
+  __syncwarp();
+}
+
+// One 32-column chunk after its accumulator values (+ bias) are in registers.  C: chunk index inside the panel
+// (compile-time, so the AdaGN group of every column is static).  `full`: tile completely inside the matrix.
+template <bool kStats, int C>
+__device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm, const EpiThread& t, float (&v)[EPI_CHUNK],
+                                          int m0, int n0, bool rows_valid, bool row_valid, float g0, float g1, float g2,
+                                          const CUtensorMap* tma_o32, const CUtensorMap* tma_o16,
+                                          float (&st)[kStats ? 32 : 1], uint32_t& cnt) {
+  const int col0 = n0 + C * EPI_CHUNK;
+  if (p.geom != nullptr) {
+    const float4* wp = reinterpret_cast<const float4*>(p.wx + (long long)col0 * 3);
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+      if (col0 + 4 * j < p.n_out) {
+        const float4 w0 = __ldg(wp + 3 * j), w1 = __ldg(wp + 3 * j + 1), w2 = __ldg(wp + 3 * j + 2);
+        v[4 * j + 0] += g0 * w0.x + g1 * w0.y + g2 * w0.z;
+        v[4 * j + 1] += g0 * w0.w + g1 * w1.x + g2 * w1.y;
+        v[4 * j + 2] += g0 * w1.z + g1 * w1.w + g2 * w2.x;
+        v[4 * j + 3] += g0 * w2.y + g1 * w2.z + g2 * w2.w;
+      }
+    }
+  }
+  if (p.act) {
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK; ++j) v[j] = fmaf(ex2_approx(v[j] * v[j] * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
+  }
+  if (p.has_res) {
+    mbar_wait(&sm.res_full[t.grp], cnt & 1u);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // two batches of four loads: latency overlapped, bounded register use
+      float4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = lds128(t.res | (((4 * h + j) << 4) ^ t.x7));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[16 * h + 4 * j + 0] += x[j].x; v[16 * h + 4 * j + 1] += x[j].y;
+        v[16 * h + 4 * j + 2] += x[j].z; v[16 * h + 4 * j + 3] += x[j].w;
+      }
+    }
+    mbar_arrive(&sm.res_empty[t.grp]);
+  }
+  if (!rows_valid && !row_valid) {
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK; ++j) v[j] = 0.f;  // padding rows stay exactly zero
+  }
+  if (kStats) {
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK; ++j) {
+      constexpr int kBase = C * EPI_CHUNK;
+      const int g = (kBase + j) / 12;  // static: n0 is a multiple of 192
+      st[2 * g] += v[j];
+      st[2 * g + 1] = fmaf(v[j], v[j], st[2 * g + 1]);
+    }
+  }
+  // stage this warp's 32 x 32 block in its private swizzled area and hand it to TMA: one bulk tensor store per
+  // output (box {32 columns, 32 rows}; rows / columns outside the matrix are clipped by the tensor map)
+  if (t.lane == 0) tma_store_wait_read<0>();  // the previous chunk's stores have finished reading the staging area
+  __syncwarp();
+  if (p.o32 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK / 4; ++j) sts128(t.w32 | ((j << 4) ^ t.x7), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (p.o16 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK / 8; ++j)
+      sts128u(t.w16 | ((j << 4) ^ t.x3), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (t.lane == 0) {
+    if (p.o32 != nullptr) tma_store_2d_addr(tma_o32, t.s32, col0, m0 + t.q * 32);
+    if (p.o16 != nullptr) tma_store_2d_addr(tma_o16, t.s16, col0, m0 + t.q * 32);
+    tma_store_commit();
+  }
+  ++cnt;
+}
+
 // Epilogue side (all threads of both groups).  taddr: TMEM address of (lane quadrant q, panel column 0).
-// grp: epilogue group of this thread, tid: 0..127 within the group; `cnt` counts the chunks this group has processed
-// (the loader keeps the same count per group).
-__device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm, const CUtensorMap* tma_o32,
-                                          const CUtensorMap* tma_o16, uint32_t taddr, int m0, int n0, int grp, int tid,
-                                          uint32_t& cnt) {
-  const int q = tid >> 5, lane = tid & 31;
-  const int r = q * 32 + lane;  // row inside the tile == TMEM lane
-  const int row = m0 + r;
-  const int cloud = (m0 + q * 32) / p.rows_per_cloud;  // warp-uniform (rows_per_cloud % 32 == 0)
-  const bool row_valid = row < p.M && (row - cloud * p.rows_per_cloud) < p.valid_rows;
+// `cnt` counts the chunks this group has processed (the loader keeps the same count per group).  epi_prefetch must
+// have been called for the same (m0, n0) by this thread.  The group's three chunks (grp, grp + 2, grp + 4) are software
+// pipelined: the TMEM load of the next chunk is issued as soon as the current one has been consumed, because
+// tcgen05.ld latency is several hundred cycles while the tensor core is streaming accumulators through TMEM.
+template <bool kStats>
+__device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm, const EpiThread& t,
+                                          const CUtensorMap* tma_o32, const CUtensorMap* tma_o16, uint32_t taddr, int m0,
+                                          int n0, uint32_t& cnt) {
+  const int row = m0 + t.q * 32 + t.lane;
+  const int cloud = (m0 + t.q * 32) / p.rows_per_cloud;  // warp-uniform (rows_per_cloud % 32 == 0)
+  const int row_in_cloud = row - cloud * p.rows_per_cloud;
+  const bool row_valid = row < p.M && row_in_cloud < p.valid_rows;
+  const bool rows_valid = m0 + t.q * 32 + 31 < p.M && (m0 + t.q * 32 + 31 - cloud * p.rows_per_cloud) < p.valid_rows;
+
+  uint32_t rr[2][EPI_CHUNK];
+  const uint32_t ta = taddr + t.grp * EPI_CHUNK;
+  if (n0 + t.grp * EPI_CHUNK < p.n_out) tmem_ld32_issue(ta, rr[0]);
 
   float g0 = 0.f, g1 = 0.f, g2 = 0.f;
   if (p.geom != nullptr && row_valid) {
     // geom is compact [clouds, valid_rows, 3]; output rows are padded to rows_per_cloud
     const float s = __ldg(p.sigma + (long long)cloud * p.sigma_stride);
     const float c_in = 1.0f / sqrtf(p.sigma_data * p.sigma_data + s * s);
-    const float* gp = p.geom + ((long long)cloud * p.valid_rows + (row - cloud * p.rows_per_cloud)) * 3;
+    const float* gp = p.geom + ((long long)cloud * p.valid_rows + row_in_cloud) * 3;
     g0 = c_in * __ldg(gp + 0);
     g1 = c_in * __ldg(gp + 1);
     g2 = c_in * __ldg(gp + 2);
   }
-  float st[32];  // [group 0..15][{sum, sumsq}] of this row over the panel
+  float st[kStats ? 32 : 1];  // [group 0..15][{sum, sumsq}] of this row over the panel
 #pragma unroll
-  for (int i = 0; i < 32; ++i) st[i] = 0.f;
-
+  for (int i = 0; i < (kStats ? 32 : 1); ++i) st[i] = 0.f;
+  auto step = [&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    if (n0 + (2 * k + t.grp) * EPI_CHUNK < p.n_out) {  // uniform over the epilogue group
+      float4 b[EPI_CHUNK / 4];
+      if (p.bias != nullptr) {
 #pragma unroll
-  for (int c = 0; c < EPI_PANEL / EPI_CHUNK; ++c) {
-    const int col0 = n0 + c * EPI_CHUNK;
-    if ((c & 1) == grp && col0 < p.n_out) {  // uniform over the epilogue group
-      uint32_t rr[EPI_CHUNK];
-      tmem_ld16(taddr + c * EPI_CHUNK, rr);
-      tmem_ld16(taddr + c * EPI_CHUNK + 16, rr + 16);
-      tmem_ld_wait();
+        for (int j = 0; j < EPI_CHUNK / 4; ++j) b[j] = lds128(t.bias + k * 128u + j * 16u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPI_CHUNK / 4; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      tmem_ld32_wait(rr[k & 1]);
       float v[EPI_CHUNK];
 #pragma unroll
-      for (int j = 0; j < EPI_CHUNK; ++j) v[j] = __uint_as_float(rr[j]);
-
-      if (p.bias != nullptr) {
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + (long long)cloud * p.bias_stride + col0);
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK / 4; ++j) {
-          if (col0 + 4 * j < p.n_out) {
-            const float4 b = __ldg(bp + j);
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
+      for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+        v[4 * j + 0] = __uint_as_float(rr[k & 1][4 * j + 0]) + b[j].x;
+        v[4 * j + 1] = __uint_as_float(rr[k & 1][4 * j + 1]) + b[j].y;
+        v[4 * j + 2] = __uint_as_float(rr[k & 1][4 * j + 2]) + b[j].z;
+        v[4 * j + 3] = __uint_as_float(rr[k & 1][4 * j + 3]) + b[j].w;
       }
-      if (p.geom != nullptr) {
-        const float4* wp = reinterpret_cast<const float4*>(p.wx + (long long)col0 * 3);
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK / 4; ++j) {
-          if (col0 + 4 * j < p.n_out) {
-            const float4 w0 = __ldg(wp + 3 * j), w1 = __ldg(wp + 3 * j + 1), w2 = __ldg(wp + 3 * j + 2);
-            v[4 * j + 0] += g0 * w0.x + g1 * w0.y + g2 * w0.z;
-            v[4 * j + 1] += g0 * w0.w + g1 * w1.x + g2 * w1.y;
-            v[4 * j + 2] += g0 * w1.z + g1 * w1.w + g2 * w2.x;
-            v[4 * j + 3] += g0 * w2.y + g1 * w2.z + g2 * w2.w;
-          }
-        }
-      }
-      if (p.act) {
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK; ++j) v[j] = (exp2f(v[j] * v[j] * p.act_k) - 0.7f) * (1.0f / 0.28f);
-      }
-      const uint32_t buf = grp, phase = cnt & 1u;
-      if (p.has_res) {
-        mbar_wait(&sm.res_full[buf], phase);
-        const uint8_t* rb = sm.res + buf * EPI_RES_BYTES;
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK / 4; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(rb + swz128(r * 128 + j * 16));
-          v[4 * j + 0] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-        }
-        mbar_arrive(&sm.res_empty[buf]);
-      }
-      if (!row_valid) {
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK; ++j) v[j] = 0.f;  // padding rows stay exactly zero
-      }
-      if (p.stats != nullptr) {
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK; ++j) {
-          const int g = (c * EPI_CHUNK + j) / 12;  // static: n0 is a multiple of 192
-          st[2 * g] += v[j];
-          st[2 * g + 1] += v[j] * v[j];
-        }
-      }
-      // the staging buffers of this group were last read by the bulk store of its previous chunk
-      if (tid == 0) tma_store_wait_read<0>();
-      named_bar_sync(EPI_BAR_FREE + 2 * grp, EPI_THREADS);
-      if (p.has_o32) {
-        uint8_t* ob = sm.o32 + buf * EPI_RES_BYTES;
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK / 4; ++j)
-          *reinterpret_cast<float4*>(ob + swz128(r * 128 + j * 16)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      if (p.has_o16) {
-        uint8_t* ob = sm.o16 + buf * EPI_O16_BYTES;
-#pragma unroll
-        for (int j = 0; j < EPI_CHUNK / 8; ++j)
-          *reinterpret_cast<uint4*>(ob + swz64(r * 64 + j * 16)) =
-              make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(EPI_BAR_STAGE + 2 * grp, EPI_THREADS);
-      if (tid == 0) {
-        if (p.has_o32) tma_store_2d(tma_o32, sm.o32 + buf * EPI_RES_BYTES, col0, m0);
-        if (p.has_o16) tma_store_2d(tma_o16, sm.o16 + buf * EPI_O16_BYTES, col0, m0);
-        tma_store_commit();
-      }
-      ++cnt;
+      if (k < 2 && n0 + (2 * k + 2 + t.grp) * EPI_CHUNK < p.n_out) tmem_ld32_issue(ta + (2 * k + 2) * EPI_CHUNK, rr[(k + 1) & 1]);
+      if (t.grp == 0)
+        epi_chunk<kStats, 2 * k>(p, sm, t, v, m0, n0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
+      else
+        epi_chunk<kStats, 2 * k + 1>(p, sm, t, v, m0, n0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
     }
-  }
-  if (p.stats != nullptr) {
-    const float mine = warp_reduce_scatter32(st, lane);
-    const int gidx = (n0 / 12) * 2 + lane;  // [group][{sum, sumsq}]
-    if (gidx < (p.n_out / 12) * 2 && m0 + q * 32 < p.M)
+  };
+  step(std::integral_constant<int, 0>{});
+  step(std::integral_constant<int, 1>{});
+  step(std::integral_constant<int, 2>{});
+  if constexpr (kStats) {
+    const float mine = warp_reduce_scatter32(st, t.lane);
+    const int gidx = (n0 / 12) * 2 + t.lane;  // [group][{sum, sumsq}]
+    if (gidx < (p.n_out / 12) * 2 && m0 + t.q * 32 < p.M)
       atomicAdd(p.stats + (long long)cloud * (p.n_out / 12) * 2 + gidx, static_cast<double>(mine));
   }
 }

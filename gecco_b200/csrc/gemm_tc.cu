@@ -10,10 +10,12 @@
 // The two TMEM slots let the epilogue of tile i overlap the main loop of tile i+1.
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <string.h>
 
 namespace gecco {
 
@@ -22,41 +24,42 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 192;
 constexpr int BK = 64;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 5;  // ring depth is chosen per launch from the shared memory the epilogue leaves
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 24 KiB
 constexpr int ACC_COLS = 256;               // TMEM columns reserved per accumulator slot
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_THREADS = 128 + EPI_GROUPS * EPI_THREADS;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_SMEM_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_LIMIT = 232448;
+constexpr int SMEM_FIXED = 1024 /*align*/ + 256 /*barriers*/;
 
 struct KParams {
   EpiParams e;
   int K, w_rows_per_cloud;
   int num_m_blocks, num_n_blocks;
+  int stages;
 };
 
+template <bool kStats>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                const __grid_constant__ CUtensorMap tma_res, const __grid_constant__ CUtensorMap tma_o32,
                const __grid_constant__ CUtensorMap tma_o16, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint8_t* sEpi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_SMEM_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;    // [2]
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
   EpiSmem es;
-  es.res = sEpi;
-  es.o32 = sEpi + EPI_GROUPS * EPI_RES_BYTES;
-  es.o16 = sEpi + 2 * EPI_GROUPS * EPI_RES_BYTES;
-  es.res_full = bars + 2 * STAGES + 4;   // [2]
-  es.res_empty = bars + 2 * STAGES + 6;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem_carve(es, sEpi, p.e.has_res, p.e.o32 != nullptr, p.e.o16 != nullptr));
+  uint64_t* full_bar = bars;                 // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;   // [MAX_STAGES]
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [2]
+  uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2;  // [2]  one arrival per epilogue warp
+  es.res_full = bars + 2 * MAX_STAGES + 4;   // [2]
+  es.res_empty = bars + 2 * MAX_STAGES + 6;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -67,17 +70,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
     if (p.e.has_res) tma_prefetch_desc(&tma_res);
-    if (p.e.has_o32) tma_prefetch_desc(&tma_o32);
-    if (p.e.has_o16) tma_prefetch_desc(&tma_o16);
+    if (p.e.o32 != nullptr) tma_prefetch_desc(&tma_o32);
+    if (p.e.o16 != nullptr) tma_prefetch_desc(&tma_o16);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_GROUPS * EPI_THREADS);
+      mbar_init(&acc_empty[i], EPI_GROUPS * EPI_THREADS / 32);
       mbar_init(&es.res_full[i], 1);
       mbar_init(&es.res_empty[i], EPI_THREADS);
     }
@@ -91,7 +94,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // everything above overlaps the tail of the preceding kernel (programmatic dependent launch)
   pdl_wait();
   pdl_launch_dependents();
+  // warps 0-3 (TMA / MMA / allocator / residual loader: a handful of registers) hand their registers to the epilogue
 
+  // warps 0-3 (TMA / MMA / allocator / residual loader: a handful of registers) hand their registers to the epilogue
+  if (warp < 4) {
+  setmaxnreg_dec<40>();
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
@@ -145,10 +152,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         epi_load_residual_panel(p.e, es, &tma_res, m0, n0, cnt);
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    setmaxnreg_inc<232>();
     // ------------------------------------------------------------ epilogue
-    const int grp = (warp - 4) >> 2;
-    const int tid = threadIdx.x & (EPI_THREADS - 1);
+    const EpiThread et = epi_thread_init(es, (warp - 4) >> 2, threadIdx.x & (EPI_THREADS - 1));
     const int q = warp & 3;  // TMEM lane quadrant of this warp
     int it = 0;
     uint32_t cnt = 0;
@@ -157,14 +165,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (t / p.num_n_blocks) * BM;
       const int n0 = (t % p.num_n_blocks) * BN;
+      epi_prefetch(p.e, et, m0, n0);
       mbar_wait(&acc_full[slot], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * ACC_COLS;
-      epi_panel(p.e, es, &tma_o32, &tma_o16, taddr, m0, n0, grp, tid, cnt);
+      epi_panel<kStats>(p.e, es, et, &tma_o32, &tma_o16, taddr, m0, n0, cnt);
       tc_fence_before_sync();
-      mbar_arrive(&acc_empty[slot]);
+      __syncwarp();
+      if (et.lane == 0) mbar_arrive(&acc_empty[slot]);  // one arrival per warp
     }
-    if (tid == 0) tma_store_wait_read<0>();
+    if (et.lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before_sync();
@@ -176,8 +186,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+bool g_use_pairs = true;
+int g_epi_skip = 0;  // gecco_set_option("gemm_pairs", 0) selects the single-CTA kernel everywhere
 
 }  // namespace
+int epi_skip_option() { return g_epi_skip; }
 
 int resolve_driver() {
   if (g_encode != nullptr) return GECCO_OK;
@@ -223,17 +236,23 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows
   return make_tmap(m, 2, ptr, cols, rows, ld * 2, 64, box_rows, 128);
 }
 
-// Tensor maps of the epilogue (epilogue.cuh): residual / fp32 output chunks {32, 128} SWIZZLE_128B, bf16 output
-// chunks {32, 128} SWIZZLE_64B.  Unused maps are filled with a copy of `dummy`.
-int make_epilogue_tmaps(const float* res, long long ldr, float* o32, long long ldo32, void* o16, long long ldo16, int m,
-                        int n_out, const CUtensorMap& dummy, CUtensorMap* tres, CUtensorMap* t32, CUtensorMap* t16) {
-  *tres = dummy; *t32 = dummy; *t16 = dummy;
+// Tensor map of the epilogue's residual prefetch (epilogue.cuh): fp32 chunks {32, 128}, SWIZZLE_128B.  Without a
+// residual the map is a copy of `dummy` (never dereferenced).
+int make_residual_tmap(const float* res, long long ldr, int m, int n_out, const CUtensorMap& dummy, CUtensorMap* tres) {
+  *tres = dummy;
   GECCO_REQUIRE(!res || ldr % 4 == 0, "residual leading dimension must be a multiple of 4");
+  if (res) return make_tmap(tres, 4, res, n_out, m, ldr * 4, EPI_CHUNK, 128, 128);
+  return GECCO_OK;
+}
+
+// Tensor maps of the epilogue's per-warp bulk stores: {32 columns, 32 rows} boxes, SWIZZLE_128B (fp32) / SWIZZLE_64B (bf16).
+int make_output_tmaps(float* o32, long long ldo32, void* o16, long long ldo16, int m, int n_out, const CUtensorMap& dummy,
+                      CUtensorMap* t32, CUtensorMap* t16) {
+  *t32 = dummy; *t16 = dummy;
   GECCO_REQUIRE(!o32 || ldo32 % 4 == 0, "fp32 output leading dimension must be a multiple of 4");
   GECCO_REQUIRE(!o16 || ldo16 % 8 == 0, "bf16 output leading dimension must be a multiple of 8");
-  if (res) if (int rc = make_tmap(tres, 4, res, n_out, m, ldr * 4, EPI_CHUNK, 128, 128)) return rc;
-  if (o32) if (int rc = make_tmap(t32, 4, o32, n_out, m, ldo32 * 4, EPI_CHUNK, 128, 128)) return rc;
-  if (o16) if (int rc = make_tmap(t16, 2, o16, n_out, m, ldo16 * 2, EPI_CHUNK, 128, 64)) return rc;
+  if (o32) if (int rc = make_tmap(t32, 4, o32, n_out, m, ldo32 * 4, EPI_CHUNK, 32, 128)) return rc;
+  if (o16) if (int rc = make_tmap(t16, 2, o16, n_out, m, ldo16 * 2, EPI_CHUNK, 32, 64)) return rc;
   return GECCO_OK;
 }
 
@@ -250,13 +269,18 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   GECCO_REQUIRE(!a.w_rows_per_cloud || a.rows_per_cloud % BM == 0,
                 "gemm: per-cloud weights need rows_per_cloud %% 128 == 0");
 
+  if (g_use_pairs) {
+    int handled = 0;
+    if (int rc = launch_gemm_pair(a, stream, &handled)) return rc;
+    if (handled) return GECCO_OK;
+  }
   const int clouds = ceil_div(a.m, a.rows_per_cloud);
   const uint64_t w_rows = a.w_rows_per_cloud ? (uint64_t)a.w_rows_per_cloud * (clouds - 1) + a.n_out : (uint64_t)a.n_out;
   CUtensorMap ta, tw, tres, t32, t16;
   if (int rc = make_tmap_bf16(&ta, a.a, a.k, a.m, a.lda, BM)) return rc;
   if (int rc = make_tmap_bf16(&tw, a.w, a.k, w_rows, a.ldw, BN)) return rc;
-  if (int rc = make_epilogue_tmaps(a.res, a.ldr, a.out_f32, a.ldo32, a.out_bf16, a.ldo16, a.m, a.n_out, ta, &tres, &t32, &t16))
-    return rc;
+  if (int rc = make_residual_tmap(a.res, a.ldr, a.m, a.n_out, ta, &tres)) return rc;
+  if (int rc = make_output_tmaps(a.out_f32, a.ldo32, a.out_bf16, a.ldo16, a.m, a.n_out, ta, &t32, &t16)) return rc;
 
   KParams p;
   p.e.M = a.m; p.e.n_out = a.n_out; p.K = a.k;
@@ -264,15 +288,22 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   p.e.bias = a.bias; p.e.bias_stride = a.bias_stride;
   p.e.act = a.act;
   p.e.act_k = a.act ? static_cast<float>(-1.4426950408889634 / (2.0 * (double)a.act_alpha * (double)a.act_alpha)) : 0.f;
-  p.e.has_res = a.res != nullptr; p.e.has_o32 = a.out_f32 != nullptr; p.e.has_o16 = a.out_bf16 != nullptr;
+  p.e.has_res = a.res != nullptr;
+  p.e.o32 = a.out_f32;
+  p.e.o16 = static_cast<__nv_bfloat16*>(a.out_bf16);
   p.e.stats = a.stats;
   p.e.geom = a.geom; p.e.sigma = a.sigma; p.e.sigma_stride = a.sigma_stride; p.e.sigma_data = a.sigma_data; p.e.wx = a.wx;
   p.num_m_blocks = ceil_div(a.m, BM);
   p.num_n_blocks = ceil_div(a.n_out, BN);
+  const int epi_bytes = epi_smem_bytes(p.e.has_res, a.out_f32 != nullptr, a.out_bf16 != nullptr);
+  p.stages = (SMEM_LIMIT - SMEM_FIXED - epi_bytes) / (A_STAGE_BYTES + B_STAGE_BYTES);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const int smem_bytes = SMEM_FIXED + epi_bytes + p.stages * (A_STAGE_BYTES + B_STAGE_BYTES);
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
     attr_set = true;
   }
@@ -281,20 +312,34 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, ta, tw, tres, t32, t16, p);
+  cudaError_t le = a.stats ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, ta, tw, tres, t32, t16, p)
+                           : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, ta, tw, tres, t32, t16, p);
   if (le != cudaSuccess) return fail_cuda(le, "gemm_tc_kernel launch");
   GECCO_CHECK_LAUNCH("gemm_tc_kernel launch");
   return GECCO_OK;
 }
 
 }  // namespace gecco
+
+extern "C" int gecco_set_option(const char* name, int value) {
+  if (name != nullptr && strcmp(name, "gemm_pairs") == 0) {
+    gecco::g_use_pairs = value != 0;
+    return GECCO_OK;
+  }
+  if (name != nullptr && strcmp(name, "epi_skip") == 0) {
+    gecco::g_epi_skip = value;
+    return GECCO_OK;
+  }
+  gecco::set_error("gecco_set_option: unknown option '%s'", name ? name : "(null)");
+  return GECCO_ERR_INVALID;
+}
 
 extern "C" int gecco_gemm(const gecco_gemm_args* args, void* stream) {
   if (args == nullptr) {

@@ -2,7 +2,21 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda.h>
+
 namespace gecco {
+
+// tensor-map builders (gemm_tc.cu)
+int make_tmap(CUtensorMap* m, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_bytes,
+              uint32_t box_cols, uint32_t box_rows, int swizzle);
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows);
+int make_output_tmaps(float* o32, long long ldo32, void* o16, long long ldo16, int m, int n_out, const CUtensorMap& dummy,
+                      CUtensorMap* t32, CUtensorMap* t16);
+int make_residual_tmap(const float* res, long long ldr, int m, int n_out, const CUtensorMap& dummy, CUtensorMap* tres);
+// CTA-pair (cta_group::2) variant of the GEMM for K <= 384 with the A tile resident in shared memory (gemm_pair.cu).
+// Returns GECCO_OK and sets *handled = 1 when the problem fits, *handled = 0 when the caller must use launch_gemm's
+// single-CTA kernel.
+int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t s, int* handled);
 
 int launch_gemm(const gecco_gemm_args& a, cudaStream_t s);
 int launch_group_stats(const float* x, long long ldx, int clouds, int rows_per_cloud, int valid_rows, int C, int gs,

@@ -38,6 +38,11 @@ const char* gecco_last_error(void);
 /* Checks that `device` is sm_100 and resolves the driver entry points. */
 int gecco_init(int device);
 
+/* Tuning / debugging switches.  "gemm_pairs" (default 1): use the CTA-pair (cta_group::2) GEMM where it applies. */
+int gecco_set_option(const char* name, int value);
+/* Development aid: device buffer ([148][16] int64) receiving per-CTA cycle counters of the CTA-pair GEMM; NULL disables. */
+int gecco_set_debug_buffer(void* buf);
+
 /* ------------------------------------------------------------------------
  * Dense projection on the tcgen05 tensor cores.
  *   out[m, n] = epilogue( sum_k a[m, k] * w[wrow(m) + n, k] )

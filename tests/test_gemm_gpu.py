@@ -98,7 +98,7 @@ def test_gemm_xyz_embed(cuda):
     assert o32.view(B, Np, C)[:, N:].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("m,n,k", [(8192, 384, 768), (148 * 128 * 2 + 128, 384, 384)])
+@pytest.mark.parametrize("m,n,k", [(8192, 384, 768), (148 * 128 * 2 + 128, 384, 384), (8192, 384, 384), (2048 * 40, 384, 320)])
 def test_gemm_persistent_residual_inplace(cuda, m, n, k):
     """Several tiles per CTA with the in-place residual stream: exercises the residual prefetch ring, the double
     buffered staging and the TMEM slot hand-over across tiles."""
@@ -153,3 +153,31 @@ def test_fold_adagn_matches_adagn_then_linear(cuda):
     got = out.view(B, Np, O)[:, :N]
     rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     assert rel < 6e-3, rel
+
+
+@pytest.mark.parametrize("pairs", [1, 0])
+def test_gemm_pair_percloud_act(cuda, pairs):
+    """K <= 384, M % 256 == 0: the CTA-pair (cta_group::2) kernel with per-cloud weights, bias and activation; the same
+    problem through the single-CTA kernel must agree."""
+    import ctypes
+
+    from gecco_b200 import _abi, ops
+
+    B, Np, N, K, C = 5, 2048, 1900, 384, 768
+    g = torch.Generator(device="cpu").manual_seed(17)
+    a = torch.randn(B * Np, K, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(B * C, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    bias = torch.randn(B, C, generator=g).to(cuda)
+    lib = _abi.load()
+    _abi.check(lib.gecco_set_option(ctypes.c_char_p(b"gemm_pairs"), pairs))
+    try:
+        _, o16 = ops.gemm(a, w, bias=bias, bias_stride=C, act_alpha=1.3, out_bf16=True, rows_per_cloud=Np, valid_rows=N,
+                          w_rows_per_cloud=C, n_out=C)
+        torch.cuda.synchronize()
+    finally:
+        _abi.check(lib.gecco_set_option(ctypes.c_char_p(b"gemm_pairs"), 1))
+    for b in range(B):
+        ref = _ref(a[b * Np:b * Np + N], w[b * C:(b + 1) * C], bias=bias[b], alpha=1.3)
+        got = o16[b * Np:b * Np + N].float()
+        assert (got - ref).abs().max().item() < 4e-2, b
+        assert o16[b * Np + N:(b + 1) * Np].abs().max().item() == 0.0
