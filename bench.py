@@ -179,6 +179,13 @@ def run_own(args):
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
 
+    # host time to enqueue one step (no synchronisation inside): if it approaches ms_per_step the run is launch-bound
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_resident()
+    host_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+
     # per-kernel-class device time of one more step, CUDA events on the launching stream
     E.profile_start()
     step_resident()
@@ -207,7 +214,7 @@ def run_own(args):
                        "parallelism": f"dp{world} (independent clouds, no data-path collective)"},
             "e2e": {"value": clouds / (ms_e2e * 1e-3), "unit": "clouds/s",
                     "h2d_bytes_per_step": images_h.numel() * 4 + K_h.numel() * 4, "d2h_bytes_per_step": out_h.numel() * 8},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / pk["tf_sustained"], "traffic": traffic,

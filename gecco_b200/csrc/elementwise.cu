@@ -119,11 +119,12 @@ __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, c
 //   AdaGN(x)[c] = a[c] x[c] + s[c],  a = scale(t) rstd_g,  s = bias(t) - a mean_g
 //   Linear(AdaGN(x))[o] = sum_c (W[o,c] a[c]) x[c] + (b[o] + sum_c W[o,c] s[c])
 // so the consumer GEMM reads the bf16 residual stream directly with per-cloud weights.  grid (row blocks, clouds),
-// 128 threads; a warp owns whole output rows (coalesced fp32 reads, 8 B bf16 writes, shuffle-reduced bias dot).
-constexpr int FOLD_ROWS = 32;
+// 256 threads; a warp owns whole output rows (coalesced fp32 reads, 8 B bf16 writes, shuffle-reduced bias dot).
+constexpr int FOLD_ROWS = 96;
 constexpr int FOLD_MAXC = 1024;
+constexpr int FOLD_THREADS = 256;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FOLD_THREADS)
 fold_adagn_kernel(const float* __restrict__ W, long long ldw, const float* __restrict__ bias, int n_out, int C,
                   const double* __restrict__ stats, int stat_gs, int groups, double count, float eps,
                   const float* __restrict__ t, int t_stride, const float* __restrict__ scale_w,
@@ -132,22 +133,30 @@ fold_adagn_kernel(const float* __restrict__ W, long long ldw, const float* __res
                   int bf_stride) {
   __shared__ __align__(16) float sa[FOLD_MAXC];
   __shared__ __align__(16) float ss[FOLD_MAXC];
+  __shared__ float smean[128], srstd[128];
   const int cloud = blockIdx.y;
   const int gs = C / groups;
   const double* cstats = stats + (long long)cloud * (C / stat_gs) * 2;
+  // group statistics once per group (the only double precision arithmetic), then per-channel coefficients in fp32
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float mean, rstd;
+    group_mean_rstd(cstats, g, gs, stat_gs, count, eps, mean, rstd);
+    smean[g] = mean;
+    srstd[g] = rstd;
+  }
+  __syncthreads();
   const float tc = __ldg(t + (long long)cloud * t_stride);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mean, rstd;
-    group_mean_rstd(cstats, c / gs, gs, stat_gs, count, eps, mean, rstd);
+    const int g = c / gs;
     const float sc = tc * __ldg(scale_w + c) + __ldg(scale_b + c);
     const float bi = tc * __ldg(bias_w + c) + __ldg(bias_b + c);
-    sa[c] = sc * rstd;
-    ss[c] = bi - sc * rstd * mean;
+    sa[c] = sc * srstd[g];
+    ss[c] = bi - sc * srstd[g] * smean[g];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o_end = min((int)(blockIdx.x + 1) * FOLD_ROWS, n_out);
-  for (int o = blockIdx.x * FOLD_ROWS + warp; o < o_end; o += 4) {
+  for (int o = blockIdx.x * FOLD_ROWS + warp; o < o_end; o += FOLD_THREADS / 32) {
     const float* wr = W + (long long)o * ldw;
     __nv_bfloat16* dst = wf + (long long)cloud * wf_cloud_stride + (long long)o * ldwf;
     float dot = 0.f;
@@ -437,9 +446,10 @@ int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s) {
   GECCO_REQUIRE(a.groups > 0 && a.c % a.groups == 0 && a.stat_gs > 0 && (a.c / a.groups) % a.stat_gs == 0,
                 "fold_adagn: group size must be a multiple of the statistics granularity");
   GECCO_REQUIRE(a.ctx_dim == 1, "fold_adagn: t_embed_dim must be 1");
+  GECCO_REQUIRE(a.groups <= 128, "fold_adagn: at most 128 groups");
   if (a.n_out == 0 || a.clouds == 0) return GECCO_OK;
   dim3 grid(ceil_div(a.n_out, FOLD_ROWS), a.clouds);
-  fold_adagn_kernel<<<grid, 128, 0, s>>>(a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
+  fold_adagn_kernel<<<grid, FOLD_THREADS, 0, s>>>(a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
                                         (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b,
                                         a.bias_w, a.bias_b, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf,
                                         a.wf_cloud_stride, a.bias_folded, a.bias_stride);

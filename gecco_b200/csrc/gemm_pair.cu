@@ -41,8 +41,11 @@ struct PParams {
   int num_kb, w_rows_per_cloud;
   int num_pair_blocks, num_n_blocks;
   int bstages;
+  int kbps;  // k-blocks per weight stage: one barrier round trip of the MMA thread per kbps * 4 MMAs
   long long* dbg;  // optional [grid][16] cycle counters (gecco_set_debug_buffer), nullptr in production
 };
+
+__device__ __forceinline__ int num_kb_of(const PParams& p) { return p.num_kb; }
 
 // cycles spent in a barrier wait, accumulated into `acc` when the debug buffer is set
 #define TIMED_WAIT(acc, bar, parity)        \
@@ -65,8 +68,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                   // [MAX_KB] resident A k-blocks
   const int BSTAGES = p.bstages;
-  uint8_t* sB = smem + MAX_KB * A_KB_BYTES;             // [BSTAGES] weight half-tiles
-  uint8_t* sEpi = sB + BSTAGES * B_STAGE_BYTES;
+  const int kbps = p.kbps;
+  const int stage_bytes = kbps * B_STAGE_BYTES;
+  const int num_st = num_kb_of(p) / kbps;
+  uint8_t* sB = smem + MAX_KB * A_KB_BYTES;             // [BSTAGES] weight half-tiles, kbps k-blocks each
+  uint8_t* sEpi = sB + BSTAGES * stage_bytes;
   EpiSmem es;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem_carve(es, sEpi, p.e.has_res, p.e.o32 != nullptr, p.e.o16 != nullptr));
   uint64_t* a_full = bars;                    // [MAX_KB]   leader: both CTAs' A k-block landed
@@ -134,16 +140,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int cloud_w = p.w_rows_per_cloud ? (m0 / p.e.rows_per_cloud) * p.w_rows_per_cloud : 0;
       for (int nb = 0; nb < p.num_n_blocks; ++nb) {
         const int wrow = cloud_w + nb * BN + (int)rank * BNH;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (nb == 0) {
-            // this CTA's 128 rows of A, k-block kb: resident for all column blocks of the row block
-            TIMED_WAIT(w_aempty, &a_empty[kb], (it & 1u) ^ 1u);
-            if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * A_KB_BYTES);
-            tma_load_2d_pair(sA + kb * A_KB_BYTES, &tma_a, &a_full[kb], kb * BK, m0);
-          }
+        for (int st = 0; st < num_st; ++st) {
           TIMED_WAIT(w_bempty, &b_empty[stage], bphase ^ 1u);
-          if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2 * B_STAGE_BYTES);
-          tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tma_w, &b_full[stage], kb * BK, wrow);
+          if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2 * stage_bytes);
+          for (int kk = 0; kk < kbps; ++kk) {
+            const int kb = st * kbps + kk;
+            if (nb == 0) {
+              // this CTA's 128 rows of A, k-block kb: resident for all column blocks of the row block
+              TIMED_WAIT(w_aempty, &a_empty[kb], (it & 1u) ^ 1u);
+              if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * A_KB_BYTES);
+              tma_load_2d_pair(sA + kb * A_KB_BYTES, &tma_a, &a_full[kb], kb * BK, m0);
+            }
+            tma_load_2d_pair(sB + stage * stage_bytes + kk * B_STAGE_BYTES, &tma_w, &b_full[stage], kb * BK, wrow);
+          }
           if (++stage == BSTAGES) { stage = 0; bphase ^= 1u; }
         }
       }
@@ -168,19 +177,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tc_fence_after_sync();
           const uint32_t tmem_d = tmem_base + slot * ACC_COLS;
           const bool last_nb = nb == p.num_n_blocks - 1;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            if (nb == 0) TIMED_WAIT(w_afull, &a_full[kb], it & 1u);
+          for (int st = 0; st < num_st; ++st) {
             TIMED_WAIT(w_bfull, &b_full[stage], bphase);
-            tc_fence_after_sync();
-            const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * A_KB_BYTES));
-            const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
-            long long ti0 = 0;
-            if (p.dbg != nullptr) ti0 = clock64();
+            for (int kk = 0; kk < kbps; ++kk) {
+              const int kb = st * kbps + kk;
+              if (nb == 0) TIMED_WAIT(w_afull, &a_full[kb], it & 1u);
+              tc_fence_after_sync();
+              const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * A_KB_BYTES));
+              const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * stage_bytes + kk * B_STAGE_BYTES));
+              long long ti0 = 0;
+              if (p.dbg != nullptr) ti0 = clock64();
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              if (last_nb) umma_commit_pair(&a_empty[kb]);  // the k-block may be reloaded for the next row block
+              if (p.dbg != nullptr) w_issue += clock64() - ti0;
+            }
             umma_commit_pair(&b_empty[stage]);
-            if (last_nb) umma_commit_pair(&a_empty[kb]);  // the k-block may be reloaded for the next row block
-            if (p.dbg != nullptr) w_issue += clock64() - ti0;
             if (++stage == BSTAGES) { stage = 0; bphase ^= 1u; }
           }
           umma_commit_pair(&acc_full[slot]);
@@ -277,10 +289,14 @@ int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t stream, int* handled
   p.num_n_blocks = ceil_div(a.n_out, BN);
   p.dbg = g_gemm_debug;
   const int epi_bytes = epi_smem_bytes(p.e.has_res, a.out_f32 != nullptr, a.out_bf16 != nullptr);
-  p.bstages = (SMEM_LIMIT - SMEM_FIXED - epi_bytes) / B_STAGE_BYTES;
+  const int avail = SMEM_LIMIT - SMEM_FIXED - epi_bytes;
+  p.kbps = 1;
+  for (int cand = p.num_kb; cand > 1; --cand)  // deepest weight stage that still leaves a 3-deep ring
+    if (p.num_kb % cand == 0 && avail / (cand * B_STAGE_BYTES) >= 3) { p.kbps = cand; break; }
+  p.bstages = avail / (p.kbps * B_STAGE_BYTES);
   if (p.bstages > MAX_BSTAGES) p.bstages = MAX_BSTAGES;
   GECCO_REQUIRE(p.bstages >= 2, "gemm_pair: shared memory budget");
-  const int smem_bytes = SMEM_FIXED + epi_bytes + p.bstages * B_STAGE_BYTES;
+  const int smem_bytes = SMEM_FIXED + epi_bytes + p.bstages * p.kbps * B_STAGE_BYTES;
 
   static bool attr_set = false;
   if (!attr_set) {

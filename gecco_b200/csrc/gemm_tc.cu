@@ -16,6 +16,7 @@
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <string.h>
+#include <unordered_map>
 
 namespace gecco {
 
@@ -205,10 +206,51 @@ int resolve_driver() {
   return GECCO_OK;
 }
 
+int make_tmap_uncached(CUtensorMap* m, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_bytes,
+                       uint32_t box_cols, uint32_t box_rows, int swizzle);
+
 // Row-major [rows, cols] matrix (ld_bytes between rows) viewed as a 2D tensor {cols, rows} with a
 // {box_cols, box_rows} box.  swizzle: 128 / 64 (bytes) - the box row must span exactly that many bytes or less.
+// cuTensorMapEncodeTiled costs several microseconds and the engine asks for the same few dozen maps on every
+// evaluation (the workspace is stable), so encoded maps are cached per thread.
+struct TmapKey {
+  const void* ptr;
+  uint64_t cols, rows, ld_bytes;
+  uint32_t box_cols, box_rows;
+  int elem_bytes, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && cols == o.cols && rows == o.rows && ld_bytes == o.ld_bytes && box_cols == o.box_cols &&
+           box_rows == o.box_rows && elem_bytes == o.elem_bytes && swizzle == o.swizzle;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.cols + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.rows * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (k.ld_bytes * 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+    h ^= ((uint64_t)k.box_cols << 40) ^ ((uint64_t)k.box_rows << 24) ^ ((uint64_t)k.elem_bytes << 8) ^ (uint64_t)k.swizzle;
+    return static_cast<size_t>(h);
+  }
+};
+static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> t_tmap_cache;
+
 int make_tmap(CUtensorMap* m, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_bytes,
               uint32_t box_cols, uint32_t box_rows, int swizzle) {
+  const TmapKey key{ptr, cols, rows, ld_bytes, box_cols, box_rows, elem_bytes, swizzle};
+  auto hit = t_tmap_cache.find(key);
+  if (hit != t_tmap_cache.end()) {
+    *m = hit->second;
+    return GECCO_OK;
+  }
+  if (int rc = make_tmap_uncached(m, elem_bytes, ptr, cols, rows, ld_bytes, box_cols, box_rows, swizzle)) return rc;
+  if (t_tmap_cache.size() > 8192) t_tmap_cache.clear();
+  t_tmap_cache.emplace(key, *m);
+  return GECCO_OK;
+}
+
+int make_tmap_uncached(CUtensorMap* m, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_bytes,
+                       uint32_t box_cols, uint32_t box_rows, int swizzle) {
   if (int rc = resolve_driver()) return rc;
   GECCO_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "operand pointer must be 16-byte aligned");
   GECCO_REQUIRE(ld_bytes % 16 == 0, "operand leading dimension must be a multiple of 16 bytes (got %llu)",
