@@ -46,7 +46,80 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
   }
 }
 
-__global__ void __launch_bounds__(LK_WARPS * 32) lookup_kernel(const LookupP p) {
+// Data-space point -> normalised image coordinates (reparam.diffusion_to_data + kornia project_points), then the
+// grid_sample grid value 2 uv - 1 (models/ray.py:71-82).
+__device__ __forceinline__ void lookup_coords(const LookupP& p, const float* __restrict__ xp, float c_in, float fx, float cx,
+                                              float fy, float cy, float& gx, float& gy) {
+  float g[3] = {c_in * __ldg(xp), c_in * __ldg(xp + 1), c_in * __ldg(xp + 2)};
+  float d[3];
+  if (p.reparam == 1) {  // GaussianReparam.diffusion_to_data (reparam.py:62-64)
+    for (int j = 0; j < 3; ++j) d[j] = g[j] * p.rsig[j] + p.mean[j];
+  } else if (p.reparam == 2) {  // UVLReparam.diffusion_to_data (reparam.py:166-201)
+    const float u0 = g[0] * p.rsig[0] + p.mean[0];
+    const float v0 = g[1] * p.rsig[1] + p.mean[1];
+    const float l0 = g[2] * p.rsig[2] + p.mean[2];
+    const float h = (tanhf(u0) * p.logit_scale + 1.0f) / 2.0f;
+    const float w = (tanhf(v0) * p.logit_scale + 1.0f) / 2.0f;
+    const float dep = expf(l0);
+    const float x = (h - cx) / fx, y = (w - cy) / fy;
+    float nrm = sqrtf(x * x + y * y + 1.0f);
+    nrm = fmaxf(nrm, 1e-12f);
+    d[0] = x / nrm * dep;
+    d[1] = y / nrm * dep;
+    d[2] = 1.0f / nrm * dep;
+  } else {
+    for (int j = 0; j < 3; ++j) d[j] = g[j];
+  }
+  // kornia project_points (models/ray.py:74)
+  const float z = d[2];
+  const float sc = (fabsf(z) > 1e-8f) ? 1.0f / (z + 1e-8f) : 1.0f;
+  const float u = d[0] * sc * fx + cx;
+  const float v = d[1] * sc * fy + cy;
+  gx = u * 2.0f - 1.0f;
+  gy = v * 2.0f - 1.0f;
+}
+
+// The four bilinear taps of one 8-channel chunk: issue the loads (zeros padding, align_corners=False).
+struct Taps {
+  uint4 q[4];
+  float w[4];
+};
+__device__ __forceinline__ void lookup_issue(const __nv_bfloat16* __restrict__ base, int H, int W, int C, float gx, float gy,
+                                             Taps& t) {
+  const float ix = ((gx + 1.0f) * W - 1.0f) / 2.0f;
+  const float iy = ((gy + 1.0f) * H - 1.0f) / 2.0f;
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+  const bool vx0 = x0 >= 0.f && x0 <= (float)(W - 1), vx1 = x1 >= 0.f && x1 <= (float)(W - 1);
+  const bool vy0 = y0 >= 0.f && y0 <= (float)(H - 1), vy1 = y1 >= 0.f && y1 <= (float)(H - 1);
+  const int xi0 = vx0 ? (int)x0 : 0, xi1 = vx1 ? (int)x1 : 0, yi0 = vy0 ? (int)y0 : 0, yi1 = vy1 ? (int)y1 : 0;
+  const bool tv[4] = {vx0 && vy0, vx1 && vy0, vx0 && vy1, vx1 && vy1};
+  const int to[4] = {(yi0 * W + xi0) * C, (yi0 * W + xi1) * C, (yi1 * W + xi0) * C, (yi1 * W + xi1) * C};
+  // a tap outside the map contributes 0: its weight is zeroed (non-finite coordinates give NaN weights, which the
+  // validity test turns into zeros exactly like grid_sample's padding)
+  t.w[0] = tv[0] ? (x1 - ix) * (y1 - iy) : 0.f;
+  t.w[1] = tv[1] ? (ix - x0) * (y1 - iy) : 0.f;
+  t.w[2] = tv[2] ? (x1 - ix) * (iy - y0) : 0.f;
+  t.w[3] = tv[3] ? (ix - x0) * (iy - y0) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t.q[i] = tv[i] ? __ldg(reinterpret_cast<const uint4*>(base + to[i])) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void lookup_blend(const Taps& t, float (&acc)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float f[8];
+    bf16x8_to_float(t.q[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], t.w[i], acc[j]);
+  }
+}
+
+// NCH: 8-channel chunks per lane (ceil(sum C / 256)).  Two points of a warp are in flight together (2 x NCH x 4
+// independent 16 B gathers per lane) because the kernel is bound by the latency of the L2-resident gathers.
+template <int NCH>
+__global__ void __launch_bounds__(LK_WARPS * 32, 2) lookup_kernel(const LookupP p) {
   extern __shared__ float sgrp[];  // [stat_groups][2]
   const int cloud = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -55,10 +128,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lookup_kernel(const LookupP p) 
     __syncthreads();
   }
   // fixed chunk -> (level, channel) assignment of this lane
-  const __nv_bfloat16* ch_ptr[LK_MAXCH];
-  int ch_h[LK_MAXCH], ch_w[LK_MAXCH], ch_c[LK_MAXCH], ch_col[LK_MAXCH];
+  const __nv_bfloat16* ch_ptr[NCH];
+  int ch_h[NCH], ch_w[NCH], ch_c[NCH], ch_col[NCH];
+  // statistics: a chunk of 8 channels touches at most two GroupNorm groups (group size >= 8): channels [0, bnd) belong to
+  // group gA, channels [bnd, 8) to group gA + 1
+  int bnd[NCH], gA[NCH];
+  const int gsz = p.stats != nullptr ? p.ctot / p.stat_groups : 8;
 #pragma unroll
-  for (int k = 0; k < LK_MAXCH; ++k) {
+  for (int k = 0; k < NCH; ++k) {
     const int col = (lane + 32 * k) * 8;
     ch_col[k] = col;
     ch_ptr[k] = nullptr;
@@ -73,12 +150,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lookup_kernel(const LookupP p) 
       }
       off += p.lvl_c[l];
     }
+    gA[k] = col / gsz;
+    const int next = (gA[k] + 1) * gsz - col;  // channels of this chunk that still belong to group gA
+    bnd[k] = next < 8 ? next : 8;
   }
-  float s1[LK_MAXCH][8], s2[LK_MAXCH][8];
+  float sA1[NCH], sA2[NCH], sB1[NCH], sB2[NCH];
 #pragma unroll
-  for (int k = 0; k < LK_MAXCH; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s1[k][j] = s2[k][j] = 0.f;
+  for (int k = 0; k < NCH; ++k) sA1[k] = sA2[k] = sB1[k] = sB2[k] = 0.f;
 
   float c_in = 1.f;
   if (p.sigma != nullptr) {
@@ -88,96 +166,60 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lookup_kernel(const LookupP p) 
   const float* Kc = p.K + (long long)cloud * 9;
   const float fx = __ldg(Kc + 0), cx = __ldg(Kc + 2), fy = __ldg(Kc + 4), cy = __ldg(Kc + 5);
 
-  for (int pt = blockIdx.x * LK_WARPS + warp; pt < p.points; pt += gridDim.x * LK_WARPS) {
-    const float* xp = p.xin + ((long long)cloud * p.points + pt) * 3;
-    float g[3] = {c_in * __ldg(xp), c_in * __ldg(xp + 1), c_in * __ldg(xp + 2)};
-    float d[3];
-    if (p.reparam == 1) {  // GaussianReparam.diffusion_to_data (reparam.py:62-64)
-      for (int j = 0; j < 3; ++j) d[j] = g[j] * p.rsig[j] + p.mean[j];
-    } else if (p.reparam == 2) {  // UVLReparam.diffusion_to_data (reparam.py:166-201)
-      const float u0 = g[0] * p.rsig[0] + p.mean[0];
-      const float v0 = g[1] * p.rsig[1] + p.mean[1];
-      const float l0 = g[2] * p.rsig[2] + p.mean[2];
-      const float h = (tanhf(u0) * p.logit_scale + 1.0f) / 2.0f;
-      const float w = (tanhf(v0) * p.logit_scale + 1.0f) / 2.0f;
-      const float dep = expf(l0);
-      const float x = (h - cx) / fx, y = (w - cy) / fy;
-      float nrm = sqrtf(x * x + y * y + 1.0f);
-      nrm = fmaxf(nrm, 1e-12f);
-      d[0] = x / nrm * dep;
-      d[1] = y / nrm * dep;
-      d[2] = 1.0f / nrm * dep;
-    } else {
-      for (int j = 0; j < 3; ++j) d[j] = g[j];
-    }
-    // kornia project_points (models/ray.py:74)
-    const float z = d[2];
-    const float sc = (fabsf(z) > 1e-8f) ? 1.0f / (z + 1e-8f) : 1.0f;
-    const float u = d[0] * sc * fx + cx;
-    const float v = d[1] * sc * fy + cy;
-    // grid_sample(align_corners=False) on grid = 2*uv - 1 (models/ray.py:80-82)
-    const float gx = u * 2.0f - 1.0f, gy = v * 2.0f - 1.0f;
-
-    const long long orow = (long long)cloud * p.rows_per_cloud + pt;
+  const int stride = gridDim.x * LK_WARPS;
+  for (int pt = blockIdx.x * LK_WARPS + warp; pt < p.points; pt += 2 * stride) {
+    const int pt2 = pt + stride;
+    const bool two = pt2 < p.points;
+    float gx[2], gy[2];
+    lookup_coords(p, p.xin + ((long long)cloud * p.points + pt) * 3, c_in, fx, cx, fy, cy, gx[0], gy[0]);
+    lookup_coords(p, p.xin + ((long long)cloud * p.points + (two ? pt2 : pt)) * 3, c_in, fx, cx, fy, cy, gx[1], gy[1]);
+    Taps taps[2][NCH];
 #pragma unroll
-    for (int k = 0; k < LK_MAXCH; ++k) {
-      if (ch_ptr[k] == nullptr) continue;
-      const int H = ch_h[k], W = ch_w[k], C = ch_c[k];
-      const float ix = ((gx + 1.0f) * W - 1.0f) / 2.0f;
-      const float iy = ((gy + 1.0f) * H - 1.0f) / 2.0f;
-      const float x0 = floorf(ix), y0 = floorf(iy);
-      const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
-      const bool vx0 = x0 >= 0.f && x0 <= (float)(W - 1), vx1 = x1 >= 0.f && x1 <= (float)(W - 1);
-      const bool vy0 = y0 >= 0.f && y0 <= (float)(H - 1), vy1 = y1 >= 0.f && y1 <= (float)(H - 1);
-      const float w_nw = (x1 - ix) * (y1 - iy), w_ne = (ix - x0) * (y1 - iy);
-      const float w_sw = (x1 - ix) * (iy - y0), w_se = (ix - x0) * (iy - y0);
-      const int xi0 = vx0 ? (int)x0 : 0, xi1 = vx1 ? (int)x1 : 0, yi0 = vy0 ? (int)y0 : 0, yi1 = vy1 ? (int)y1 : 0;
-      uint4 q[4];
-      const bool tv[4] = {vx0 && vy0, vx1 && vy0, vx0 && vy1, vx1 && vy1};
-      const int to[4] = {(yi0 * W + xi0) * C, (yi0 * W + xi1) * C, (yi1 * W + xi0) * C, (yi1 * W + xi1) * C};
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        q[t] = tv[t] ? __ldg(reinterpret_cast<const uint4*>(ch_ptr[k] + to[t])) : make_uint4(0, 0, 0, 0);
-      const float tw[4] = {w_nw, w_ne, w_sw, w_se};
-      float acc[8];
+      for (int k = 0; k < NCH; ++k)
+        if (ch_ptr[k] != nullptr) lookup_issue(ch_ptr[k], ch_h[k], ch_w[k], ch_c[k], gx[h], gy[h], taps[h][k]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long orow = (long long)cloud * p.rows_per_cloud + (h ? pt2 : pt);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (tv[t]) {
-          float f[8];
-          bf16x8_to_float(q[t], f);
+      for (int k = 0; k < NCH; ++k) {
+        if (ch_ptr[k] == nullptr) continue;
+        float acc[8];
+        lookup_blend(taps[h][k], acc);
+        if (p.stats != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += f[j] * tw[t];
+          for (int j = 0; j < 8; ++j) {
+            const bool inA = j < bnd[k];
+            sA1[k] += inA ? acc[j] : 0.f;
+            sA2[k] += inA ? acc[j] * acc[j] : 0.f;
+            sB1[k] += inA ? 0.f : acc[j];
+            sB2[k] += inA ? 0.f : acc[j] * acc[j];
+          }
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[k][j] += acc[j];
-        s2[k][j] += acc[j] * acc[j];
-      }
-      if (p.out16 != nullptr) {
-        *reinterpret_cast<uint4*>(p.out16 + orow * p.ldo16 + ch_col[k]) =
-            make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                       pack_bf16x2(acc[6], acc[7]));
-      }
-      if (p.out32 != nullptr) {
-        float4* o = reinterpret_cast<float4*>(p.out32 + orow * p.ldo32 + ch_col[k]);
-        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        if (p.out16 != nullptr) {
+          *reinterpret_cast<uint4*>(p.out16 + orow * p.ldo16 + ch_col[k]) =
+              make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                         pack_bf16x2(acc[6], acc[7]));
+        }
+        if (p.out32 != nullptr) {
+          float4* o = reinterpret_cast<float4*>(p.out32 + orow * p.ldo32 + ch_col[k]);
+          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
       }
     }
   }
   if (p.stats != nullptr) {
-    const int gsz = p.ctot / p.stat_groups;
 #pragma unroll
-    for (int k = 0; k < LK_MAXCH; ++k) {
+    for (int k = 0; k < NCH; ++k) {
       if (ch_ptr[k] == nullptr) continue;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (ch_col[k] + j) / gsz;
-        atomicAdd(&sgrp[g * 2], s1[k][j]);
-        atomicAdd(&sgrp[g * 2 + 1], s2[k][j]);
+      atomicAdd(&sgrp[gA[k] * 2], sA1[k]);
+      atomicAdd(&sgrp[gA[k] * 2 + 1], sA2[k]);
+      if (bnd[k] < 8) {
+        atomicAdd(&sgrp[(gA[k] + 1) * 2], sB1[k]);
+        atomicAdd(&sgrp[(gA[k] + 1) * 2 + 1], sB2[k]);
       }
     }
     __syncthreads();
@@ -188,31 +230,40 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lookup_kernel(const LookupP p) 
 
 // GroupNorm (no affine) followed by Linear, folded per cloud (models/ray.py:52-55):
 //   Linear(GN(z))[o] = sum_c (W[o,c] rstd_g(c)) z[c] + (b[o] - sum_c W[o,c] mean_g(c) rstd_g(c))
-__global__ void fold_gn_kernel(const float* __restrict__ W, const float* __restrict__ bias,
-                               const double* __restrict__ stats, double count, float eps, int groups, int c_in,
-                               int c_out, __nv_bfloat16* __restrict__ wb, long long ldwb, float* __restrict__ bb) {
-  __shared__ float red[32];
-  const int o = blockIdx.x, cloud = blockIdx.y;
+constexpr int FGN_ROWS = 16;  // output rows per block (4 warps x 4)
+
+__global__ void __launch_bounds__(128)
+fold_gn_kernel(const float* __restrict__ W, const float* __restrict__ bias, const double* __restrict__ stats, double count,
+               float eps, int groups, int c_in, int c_out, __nv_bfloat16* __restrict__ wb, long long ldwb,
+               float* __restrict__ bb) {
+  __shared__ float smean[64], srstd[64];
+  const int cloud = blockIdx.y;
   const int gs = c_in / groups;
   const double* cs = stats + (long long)cloud * groups * 2;
-  float acc = 0.f;
-  for (int c = threadIdx.x; c < c_in; c += blockDim.x) {
-    const int g = c / gs;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {  // the only double precision arithmetic
     const double m = cs[g * 2] / count;
     double var = cs[g * 2 + 1] / count - m * m;
     if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + (double)eps));
-    const float w = __ldg(W + (long long)o * c_in + c) * rstd;
-    wb[((long long)cloud * c_out + o) * ldwb + c] = __float2bfloat16(w);
-    acc += w * static_cast<float>(m);
+    smean[g] = static_cast<float>(m);
+    srstd[g] = static_cast<float>(1.0 / sqrt(var + (double)eps));
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) bb[(long long)cloud * c_out + o] = __ldg(bias + o) - v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o_end = min((int)(blockIdx.x + 1) * FGN_ROWS, c_out);
+  for (int o = blockIdx.x * FGN_ROWS + warp; o < o_end; o += 4) {
+    const float* wr = W + (long long)o * c_in;
+    __nv_bfloat16* dst = wb + ((long long)cloud * c_out + o) * ldwb;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = lane * 2; c < c_in; c += 64) {
+      const float2 w2 = __ldg(reinterpret_cast<const float2*>(wr + c));
+      const int g0 = c / gs, g1 = (c + 1) / gs;
+      const float w0 = w2.x * srstd[g0], w1 = w2.y * srstd[g1];
+      *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16x2(w0, w1);
+      acc += w0 * smean[g0] + w1 * smean[g1];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) bb[(long long)cloud * c_out + o] = __ldg(bias + o) - acc;
   }
 }
 
@@ -268,16 +319,23 @@ int launch_lookup(const gecco_lookup_args& a, cudaStream_t s) {
   p.out32 = a.out_f32; p.ldo32 = a.ldo32;
   p.stats = a.stats; p.stat_groups = a.stats ? a.stat_groups : 0;
   if (a.points == 0 || a.clouds == 0) return GECCO_OK;
+  GECCO_REQUIRE(!a.stats || ctot / a.stat_groups >= 8, "lookup: GroupNorm groups must be at least 8 channels wide");
   dim3 grid(ceil_div(a.points, LK_WARPS * LK_POINTS_PER_WARP), a.clouds);
-  lookup_kernel<<<grid, LK_WARPS * 32, p.stat_groups * 2 * sizeof(float), s>>>(p);
+  const size_t sm = p.stat_groups * 2 * sizeof(float);
+  switch (ceil_div(ctot, 256)) {
+    case 1: lookup_kernel<1><<<grid, LK_WARPS * 32, sm, s>>>(p); break;
+    case 2: lookup_kernel<2><<<grid, LK_WARPS * 32, sm, s>>>(p); break;
+    case 3: lookup_kernel<3><<<grid, LK_WARPS * 32, sm, s>>>(p); break;
+    default: lookup_kernel<4><<<grid, LK_WARPS * 32, sm, s>>>(p); break;
+  }
   GECCO_CHECK_LAUNCH("lookup_kernel");
   return GECCO_OK;
 }
 
 int launch_fold_gn(const float* W, const float* bias, const double* stats, double count, float eps, int groups,
                    int c_in, int c_out, int clouds, void* wb, long long ldwb, float* bb, cudaStream_t s) {
-  GECCO_REQUIRE(groups > 0 && c_in % groups == 0, "fold_gn: bad groups");
-  dim3 grid(c_out, clouds);
+  GECCO_REQUIRE(groups > 0 && groups <= 64 && c_in % groups == 0 && c_in % 2 == 0 && ldwb % 2 == 0, "fold_gn: bad layout");
+  dim3 grid(ceil_div(c_out, FGN_ROWS), clouds);
   fold_gn_kernel<<<grid, 128, 0, s>>>(W, bias, stats, count, eps, groups, c_in, c_out,
                                       static_cast<__nv_bfloat16*>(wb), ldwb, bb);
   GECCO_CHECK_LAUNCH("fold_gn_kernel");
