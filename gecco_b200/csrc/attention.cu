@@ -39,6 +39,13 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// ex2.approx: one MUFU instruction (exp2f adds range handling that softmax on max-subtracted scores does not need;
+// ex2.approx(-inf) = +0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -58,9 +65,11 @@ pool_attn_kernel(const __nv_bfloat16* __restrict__ kv, long long ld, int k_off, 
                  int valid_rows, const __nv_bfloat16* __restrict__ q_ind, float* __restrict__ part, int tiles_per_split) {
   constexpr int LDS = D + PAD;
   constexpr int CH = D / 8;  // 16-byte chunks per row
-  __shared__ __align__(16) __nv_bfloat16 sQ[NI][LDS];
-  __shared__ __align__(16) __nv_bfloat16 sK[2][KT][LDS];
-  __shared__ __align__(16) __nv_bfloat16 sV[2][KT][LDS];
+  constexpr int PS = 3;  // cp.async stages: two key tiles in flight while one is consumed, one barrier per tile
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  __nv_bfloat16(*sQ)[LDS] = reinterpret_cast<__nv_bfloat16(*)[LDS]>(pool_smem);
+  __nv_bfloat16(*sK)[KT][LDS] = reinterpret_cast<__nv_bfloat16(*)[KT][LDS]>(pool_smem + NI * LDS * 2);
+  __nv_bfloat16(*sV)[KT][LDS] = reinterpret_cast<__nv_bfloat16(*)[KT][LDS]>(pool_smem + (NI + PS * KT) * LDS * 2);
 
   const int split = blockIdx.x, head = blockIdx.y, cloud = blockIdx.z;
   const int nsplit = gridDim.x, heads = gridDim.y;
@@ -91,6 +100,8 @@ pool_attn_kernel(const __nv_bfloat16* __restrict__ kv, long long ld, int k_off, 
   }
   if (tile0 < tile1) stage(0, tile0);
   cp_async_commit();
+  if (tile0 + 1 < tile1) stage(1, tile0 + 1);
+  cp_async_commit();
   __syncthreads();
   uint32_t aQ[D / 16][4];
 #pragma unroll
@@ -104,11 +115,11 @@ pool_attn_kernel(const __nv_bfloat16* __restrict__ kv, long long ld, int k_off, 
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
   for (int tile = tile0; tile < tile1; ++tile) {
-    const int buf = (tile - tile0) & 1;
-    if (tile + 1 < tile1) stage(buf ^ 1, tile + 1);
+    const int buf = (tile - tile0) % PS;
+    cp_async_wait<1>();  // tile `tile` has landed (at most the group of tile + 1 is still in flight)
+    __syncthreads();     // ... for every thread, and everybody is done with the buffer tile + 2 is about to overwrite
+    if (tile + 2 < tile1) stage((buf + 2) % PS, tile + 2);
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
 
     // S = Q K^T  (16 x 64 per warp)
     float sacc[KT / 8][4];
@@ -143,7 +154,7 @@ pool_attn_kernel(const __nv_bfloat16* __restrict__ kv, long long ld, int k_off, 
     for (int r = 0; r < 2; ++r) {
       const float mnew = fmaxf(m_run[r], quad_max(tmax[r]));
       muse[r] = (mnew == -INFINITY) ? 0.f : mnew;
-      alpha[r] = exp2f(m_run[r] - muse[r]);
+      alpha[r] = fast_exp2(m_run[r] - muse[r]);
       m_run[r] = mnew;
       l_run[r] *= alpha[r];
     }
@@ -155,8 +166,8 @@ pool_attn_kernel(const __nv_bfloat16* __restrict__ kv, long long ld, int k_off, 
     uint32_t aP[KT / 16][4];
 #pragma unroll
     for (int nb = 0; nb < KT / 8; ++nb) {
-      const float p0 = exp2f(sacc[nb][0] - muse[0]), p1 = exp2f(sacc[nb][1] - muse[0]);
-      const float p2 = exp2f(sacc[nb][2] - muse[1]), p3 = exp2f(sacc[nb][3] - muse[1]);
+      const float p0 = fast_exp2(sacc[nb][0] - muse[0]), p1 = fast_exp2(sacc[nb][1] - muse[0]);
+      const float p2 = fast_exp2(sacc[nb][2] - muse[1]), p3 = fast_exp2(sacc[nb][3] - muse[1]);
       l_run[0] += p0 + p1;
       l_run[1] += p2 + p3;
       aP[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -174,7 +185,6 @@ pool_attn_kernel(const __nv_bfloat16* __restrict__ kv, long long ld, int k_off, 
         mma16816(oacc[nb + 1], aP[ks], b[2], b[3]);
       }
     }
-    __syncthreads();
   }
   cp_async_wait<0>();
 
@@ -211,7 +221,7 @@ __global__ void pool_combine_kernel(const float* __restrict__ part, int heads, i
   for (int s = 0; s < nsplit; ++s) {
     const float* pr = base + ((long long)s * NI + i) * (D + 2);
     const float m = pr[D];
-    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    const float w = (m == -INFINITY) ? 0.f : fast_exp2(m - M);
     L += w * pr[D + 1];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -310,8 +320,8 @@ unpool_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __n
     uint32_t aP[NI / 16][4];
 #pragma unroll
     for (int nb = 0; nb < NI / 8; ++nb) {
-      const float p0 = exp2f(sacc[nb][0] - mx[0]), p1 = exp2f(sacc[nb][1] - mx[0]);
-      const float p2 = exp2f(sacc[nb][2] - mx[1]), p3 = exp2f(sacc[nb][3] - mx[1]);
+      const float p0 = fast_exp2(sacc[nb][0] - mx[0]), p1 = fast_exp2(sacc[nb][1] - mx[0]);
+      const float p2 = fast_exp2(sacc[nb][2] - mx[1]), p3 = fast_exp2(sacc[nb][3] - mx[1]);
       sum[0] += p0 + p1;
       sum[1] += p2 + p3;
       aP[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -369,10 +379,19 @@ int launch_pool_attention(const gecco_pool_args& a, cudaStream_t s) {
   dim3 grid(a.splits, a.heads, a.clouds);
   const __nv_bfloat16* kv = static_cast<const __nv_bfloat16*>(a.kv);
   const __nv_bfloat16* qi = static_cast<const __nv_bfloat16*>(a.q_inducers);
+  const int smem = (NI + 2 * 3 * KT) * (a.head_dim + PAD) * 2;  // sQ + 3 stages of K and V
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pool_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pool_attn_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pool_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(pool_attn_kernel)");
+    attr_set = true;
+  }
   switch (a.head_dim) {
-    case 32: pool_attn_kernel<32><<<grid, 128, 0, s>>>(kv, a.ld, a.k_off, a.v_off, a.rows_per_cloud, a.valid_rows, qi, a.partial, tps); break;
-    case 48: pool_attn_kernel<48><<<grid, 128, 0, s>>>(kv, a.ld, a.k_off, a.v_off, a.rows_per_cloud, a.valid_rows, qi, a.partial, tps); break;
-    default: pool_attn_kernel<64><<<grid, 128, 0, s>>>(kv, a.ld, a.k_off, a.v_off, a.rows_per_cloud, a.valid_rows, qi, a.partial, tps); break;
+    case 32: pool_attn_kernel<32><<<grid, 128, smem, s>>>(kv, a.ld, a.k_off, a.v_off, a.rows_per_cloud, a.valid_rows, qi, a.partial, tps); break;
+    case 48: pool_attn_kernel<48><<<grid, 128, smem, s>>>(kv, a.ld, a.k_off, a.v_off, a.rows_per_cloud, a.valid_rows, qi, a.partial, tps); break;
+    default: pool_attn_kernel<64><<<grid, 128, smem, s>>>(kv, a.ld, a.k_off, a.v_off, a.rows_per_cloud, a.valid_rows, qi, a.partial, tps); break;
   }
   GECCO_CHECK_LAUNCH("pool_attn_kernel");
   const int rows = a.clouds * a.heads * NI;
