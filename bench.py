@@ -191,7 +191,7 @@ def run_own(args):
     step_resident()
     prof = E.profile_stop()
     total_prof_ms = sum(p["ms"] for p in prof)
-    gemm = [p for p in prof if p["name"].startswith("gemm_")]
+    gemm = [p for p in prof if p["name"].startswith("gemm_") or p["name"].endswith("_fused")]
     gemm_ms, gemm_flops = sum(p["ms"] for p in gemm), sum(p["flops"] for p in gemm)
     pk = peaks()
     # the dominant kernel: the CTA-pair tcgen05 GEMM of the k|v|q projection (most expensive launch of an evaluation)

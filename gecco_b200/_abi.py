@@ -36,6 +36,23 @@ class GemmArgs(C.Structure):
     ]
 
 
+class MlpArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64),
+        ("w1", C.c_void_p), ("ldw1", C.c_int64), ("w1_rows_per_cloud", C.c_int32),
+        ("b1", C.c_void_p), ("b1_stride", C.c_int32),
+        ("act_alpha", C.c_float),
+        ("w2", C.c_void_p), ("ldw2", C.c_int64),
+        ("b2", C.c_void_p),
+        ("m", C.c_int32), ("c", C.c_int32), ("hidden", C.c_int32),
+        ("rows_per_cloud", C.c_int32), ("valid_rows", C.c_int32),
+        ("res", C.c_void_p), ("ldr", C.c_int64),
+        ("out_f32", C.c_void_p), ("ldo32", C.c_int64),
+        ("out_bf16", C.c_void_p), ("ldo16", C.c_int64),
+        ("stats", C.c_void_p),
+    ]
+
+
 class AdaGNArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ldx", C.c_int64),

@@ -7,6 +7,7 @@
 
 #include <math.h>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -18,11 +19,11 @@ namespace gecco {
 namespace {
 enum KClass {
   K_PREP = 0, K_LIFT, K_LOOKUP, K_FOLD_GN, K_GEMM_IMG, K_FOLD_ADAGN, K_GEMM_KVQ, K_POOL_ATTN, K_INDUCER_CHAIN,
-  K_UNPOOL_ATTN, K_GEMM_UNPOOL_OUT, K_GEMM_MLP0, K_GEMM_MLP2, K_HEAD, K_MISC, K_COUNT
+  K_UNPOOL_ATTN, K_GEMM_UNPOOL_OUT, K_GEMM_MLP0, K_GEMM_MLP2, K_MLP_FUSED, K_HEAD, K_MISC, K_COUNT
 };
 const char* const kClassNames[K_COUNT] = {
     "prep", "lift", "lookup", "fold_group_norm", "gemm_img_proj", "fold_adagn", "gemm_kv_q", "pool_attention",
-    "inducer_chain", "unpool_attention", "gemm_unpool_out", "gemm_mlp_up_act", "gemm_mlp_down",
+    "inducer_chain", "unpool_attention", "gemm_unpool_out", "gemm_mlp_up_act", "gemm_mlp_down", "mlp_fused",
     "head_edm_step", "misc"};
 struct Profiler {
   bool on = false;
@@ -240,6 +241,16 @@ gecco_fold_adagn_args fold_base(const gecco_engine* e, const float* const* nw /*
   return a;
 }
 
+// GECCO_FUSED_MLP=1 routes the point-side MLP through the single fused kernel (mlp_fused.cu).  Off by default: at the
+// bench shape the fused kernel (446 us / layer) is still slower than the two pair GEMMs (253 us / layer), see DESIGN.md.
+bool fused_mlp_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("GECCO_FUSED_MLP");
+    return v != nullptr && v[0] == '1';
+  }();
+  return on;
+}
+
 #define TRY(expr)            \
   do {                       \
     int rc__ = (expr);       \
@@ -412,17 +423,32 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       f.w_folded_bf16 = w.wfold; f.ldwf = C; f.wf_cloud_stride = (long long)hid * C;
       f.bias_folded = w.bfold; f.bias_stride = hid;
       TRYP(K_FOLD_ADAGN, 2.0 * clouds * Hd * Cd, Hd * Cd * (4.0 + 2.0 * clouds), launch_fold_adagn(f, s));
-      gecco_gemm_args g = gemm_base(w.xb, C, w.wfold, C, rows, hid, C, Np, points);
-      g.w_rows_per_cloud = hid;
-      g.bias = w.bfold; g.bias_stride = hid; g.act = 1; g.act_alpha = L.mlp_alpha;
-      g.out_bf16 = w.big; g.ldo16 = hid;
-      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd + Hd) * 2 + 2.0 * clouds * Cd * Hd, launch_gemm(g, s));
-      g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
-      g.bias = lw[GECCO_LW_MLP_B2];
-      g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
-      g.out_bf16 = w.xb; g.ldo16 = C;
-      g.stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
-      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 10) + 2 * Cd * Hd, launch_gemm(g, s));
+      double* next_stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
+      gecco_mlp_args m = {};
+      m.a = w.xb; m.lda = C;
+      m.w1 = w.wfold; m.ldw1 = C; m.w1_rows_per_cloud = hid;
+      m.b1 = w.bfold; m.b1_stride = hid;
+      m.act_alpha = L.mlp_alpha;
+      m.w2 = L.mlp_w2; m.ldw2 = hid; m.b2 = lw[GECCO_LW_MLP_B2];
+      m.m = rows; m.c = C; m.hidden = hid; m.rows_per_cloud = Np; m.valid_rows = points;
+      m.res = w.x; m.ldr = C; m.out_f32 = w.x; m.ldo32 = C; m.out_bf16 = w.xb; m.ldo16 = C;
+      m.stats = next_stats;
+      if (fused_mlp_enabled() && mlp_fused_supported(m)) {
+        // one kernel, hidden activation on chip (mlp_fused.cu)
+        TRYP(K_MLP_FUSED, 4 * Mv * Cd * Hd, Mv * Cd * 12 + 2.0 * clouds * Cd * Hd + 2 * Cd * Hd, launch_mlp_fused(m, s));
+      } else {
+        gecco_gemm_args g = gemm_base(w.xb, C, w.wfold, C, rows, hid, C, Np, points);
+        g.w_rows_per_cloud = hid;
+        g.bias = w.bfold; g.bias_stride = hid; g.act = 1; g.act_alpha = L.mlp_alpha;
+        g.out_bf16 = w.big; g.ldo16 = hid;
+        TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd + Hd) * 2 + 2.0 * clouds * Cd * Hd, launch_gemm(g, s));
+        g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
+        g.bias = lw[GECCO_LW_MLP_B2];
+        g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
+        g.out_bf16 = w.xb; g.ldo16 = C;
+        g.stats = next_stats;
+        TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 10) + 2 * Cd * Hd, launch_gemm(g, s));
+      }
     }
   }
 

@@ -40,6 +40,8 @@ struct EpiParams {
   int sigma_stride;
   float sigma_data;
   const float* wx;  // [n_out, 3]
+  int skip;         // development aid (gecco_set_option("epi_skip")): 1 no output stores, 2 no residual, 4 no proxy fence, 8 no statistics atomics
+  long long* dbg;   // development aid: [grid][32] cycle counters, slots 16..21 (nullptr in production)
 };
 
 struct EpiSmem {
@@ -185,6 +187,17 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiThread
   __syncwarp();
 }
 
+#define EPI_TIMED(slot, stmt)                                                        \
+  do {                                                                              \
+    if (p.dbg != nullptr) {                                                         \
+      const long long t0__ = clock64();                                             \
+      stmt;                                                                         \
+      if (t.lane == 0 && t.q == 0 && t.grp == 0) p.dbg[(long long)blockIdx.x * 32 + (slot)] += clock64() - t0__; \
+    } else {                                                                        \
+      stmt;                                                                         \
+    }                                                                               \
+  } while (0)
+
 // One 32-column chunk after its accumulator values (+ bias) are in registers.  C: chunk index inside the panel
 // (compile-time, so the AdaGN group of every column is static).  `full`: tile completely inside the matrix.
 template <bool kStats, int C>
@@ -210,8 +223,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
 #pragma unroll
     for (int j = 0; j < EPI_CHUNK; ++j) v[j] = fmaf(ex2_approx(v[j] * v[j] * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
   }
-  if (p.has_res) {
-    mbar_wait(&sm.res_full[t.grp], cnt & 1u);
+  if (p.has_res && !(p.skip & 2)) {
+    EPI_TIMED(17, mbar_wait(&sm.res_full[t.grp], cnt & 1u));
 #pragma unroll
     for (int h = 0; h < 2; ++h) {  // two batches of four loads: latency overlapped, bounded register use
       float4 x[4];
@@ -240,8 +253,9 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
   }
   // stage this warp's 32 x 32 block in its private swizzled area and hand it to TMA: one bulk tensor store per
   // output (box {32 columns, 32 rows}; rows / columns outside the matrix are clipped by the tensor map)
-  if (t.lane == 0) tma_store_wait_read<0>();  // the previous chunk's stores have finished reading the staging area
-  __syncwarp();
+  EPI_TIMED(18, { if (t.lane == 0) tma_store_wait_read<0>(); __syncwarp(); });  // previous chunk's stores have read the staging area
+  long long tf0__ = 0;
+  if (p.dbg != nullptr) tf0__ = clock64();
   if (p.o32 != nullptr) {
 #pragma unroll
     for (int j = 0; j < EPI_CHUNK / 4; ++j) sts128(t.w32 | ((j << 4) ^ t.x7), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -252,12 +266,21 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
       sts128u(t.w16 | ((j << 4) ^ t.x3), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
   }
-  fence_proxy_async_smem();
+  long long tf1__ = 0, tf2__ = 0;
+  if (p.dbg != nullptr) tf1__ = clock64();
+  if (!(p.skip & 4)) fence_proxy_async_smem();
   __syncwarp();
-  if (t.lane == 0) {
+  if (p.dbg != nullptr) tf2__ = clock64();
+  if (t.lane == 0 && !(p.skip & 1)) {
     if (p.o32 != nullptr) tma_store_2d_addr(tma_o32, t.s32, col0, m0 + t.q * 32);
     if (p.o16 != nullptr) tma_store_2d_addr(tma_o16, t.s16, col0, m0 + t.q * 32);
     tma_store_commit();
+  }
+  if (p.dbg != nullptr && t.lane == 0 && t.q == 0 && t.grp == 0) {
+    const long long tf3__ = clock64();
+    p.dbg[(long long)blockIdx.x * 32 + 19] += tf1__ - tf0__;
+    p.dbg[(long long)blockIdx.x * 32 + 29] += tf2__ - tf1__;
+    p.dbg[(long long)blockIdx.x * 32 + 30] += tf3__ - tf2__;
   }
   ++cnt;
 }
@@ -305,7 +328,7 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
 #pragma unroll
         for (int j = 0; j < EPI_CHUNK / 4; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      tmem_ld32_wait(rr[k & 1]);
+      EPI_TIMED(16, tmem_ld32_wait(rr[k & 1]));
       float v[EPI_CHUNK];
 #pragma unroll
       for (int j = 0; j < EPI_CHUNK / 4; ++j) {
@@ -325,10 +348,13 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
   step(std::integral_constant<int, 1>{});
   step(std::integral_constant<int, 2>{});
   if constexpr (kStats) {
+    long long ts0__ = 0;
+    if (p.dbg != nullptr) ts0__ = clock64();
     const float mine = warp_reduce_scatter32(st, t.lane);
     const int gidx = (n0 / 12) * 2 + t.lane;  // [group][{sum, sumsq}]
     if (gidx < (p.n_out / 12) * 2 && m0 + t.q * 32 < p.M)
-      atomicAdd(p.stats + (long long)cloud * (p.n_out / 12) * 2 + gidx, static_cast<double>(mine));
+      if (!(p.skip & 8)) atomicAdd(p.stats + (long long)cloud * (p.n_out / 12) * 2 + gidx, static_cast<double>(mine));
+    if (p.dbg != nullptr && t.lane == 0 && t.q == 0 && t.grp == 0) p.dbg[(long long)blockIdx.x * 32 + 20] += clock64() - ts0__;
   }
 }
 

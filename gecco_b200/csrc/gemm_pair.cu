@@ -205,7 +205,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 3 && lane == 0) {
     // ------------------------------------------------------------ residual loader
-    if (p.e.has_res) {
+    if (p.e.has_res && !(p.e.skip & 2)) {
       uint32_t cnt[EPI_GROUPS] = {0, 0};
       for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs) {
         const int m0 = pb * 2 * BM + (int)rank * BM;
@@ -288,6 +288,8 @@ int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t stream, int* handled
   p.num_pair_blocks = a.m / (2 * BM);
   p.num_n_blocks = ceil_div(a.n_out, BN);
   p.dbg = g_gemm_debug;
+  p.e.dbg = g_gemm_debug;
+  p.e.skip = epi_skip_option();
   const int epi_bytes = epi_smem_bytes(p.e.has_res, a.out_f32 != nullptr, a.out_bf16 != nullptr);
   const int avail = SMEM_LIMIT - SMEM_FIXED - epi_bytes;
   p.kbps = 1;

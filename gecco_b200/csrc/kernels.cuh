@@ -19,6 +19,9 @@ int make_residual_tmap(const float* res, long long ldr, int m, int n_out, const 
 int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t s, int* handled);
 
 int launch_gemm(const gecco_gemm_args& a, cudaStream_t s);
+// Fused MLP (mlp_fused.cu): GEMM -> Gaussian activation -> GEMM -> + residual with the hidden tensor on chip.
+bool mlp_fused_supported(const gecco_mlp_args& a);
+int launch_mlp_fused(const gecco_mlp_args& a, cudaStream_t s);
 int launch_group_stats(const float* x, long long ldx, int clouds, int rows_per_cloud, int valid_rows, int C, int gs,
                        double* stats, cudaStream_t s);
 int launch_adagn(const gecco_adagn_args& a, cudaStream_t s);

@@ -102,6 +102,50 @@ def gemm(
     return out_f32, out_bf16
 
 
+def mlp(a: Tensor, w1: Tensor, b1: Tensor, act_alpha: float, w2: Tensor, b2: Tensor, res: Tensor, *,
+        out_f32: Tensor | None = None, out_bf16: Tensor | bool | None = None, stats: Tensor | None = None,
+        rows_per_cloud: int | None = None, valid_rows: int | None = None, w1_rows_per_cloud: int = 0,
+        b1_stride: int = 0):
+    """out = res + w2 @ g(w1_cloud @ a + b1_cloud) + b2 with the hidden activation kept on chip; see gecco_mlp in
+    include/gecco_b200.h (models/set_transformer.py:165-166)."""
+    lib = _lib_for(a)
+    assert a.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert a.dim() == 2 and a.stride(1) == 1 and w1.stride(1) == 1 and w2.stride(1) == 1
+    assert b1.dtype == torch.float32 and b2.dtype == torch.float32 and res.dtype == torch.float32 and res.stride(1) == 1
+    m, c = a.shape
+    hidden = w2.shape[1]
+    if rows_per_cloud is None:
+        rows_per_cloud, valid_rows = m, m
+    if valid_rows is None:
+        valid_rows = rows_per_cloud
+    if out_f32 is None:
+        out_f32 = torch.empty((m, c), device=a.device, dtype=torch.float32)
+    if out_bf16 is True:
+        out_bf16 = torch.empty((m, c), device=a.device, dtype=torch.bfloat16)
+    if out_bf16 is False:
+        out_bf16 = None
+    args = _abi.MlpArgs()
+    args.a, args.lda = a.data_ptr(), a.stride(0)
+    args.w1, args.ldw1, args.w1_rows_per_cloud = w1.data_ptr(), w1.stride(0), w1_rows_per_cloud
+    args.b1, args.b1_stride = b1.data_ptr(), b1_stride
+    args.act_alpha = float(act_alpha)
+    args.w2, args.ldw2 = w2.data_ptr(), w2.stride(0)
+    args.b2 = b2.data_ptr()
+    args.m, args.c, args.hidden = m, c, hidden
+    args.rows_per_cloud, args.valid_rows = rows_per_cloud, valid_rows
+    args.res, args.ldr = res.data_ptr(), res.stride(0)
+    assert out_f32.dtype == torch.float32 and out_f32.stride(1) == 1
+    args.out_f32, args.ldo32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_bf16 is not None:
+        assert out_bf16.dtype == torch.bfloat16 and out_bf16.stride(1) == 1
+        args.out_bf16, args.ldo16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if stats is not None:
+        assert stats.dtype == torch.float64 and stats.is_contiguous()
+        args.stats = stats.data_ptr()
+    _abi.check(lib.gecco_mlp(C.byref(args), _stream(a)))
+    return out_f32, out_bf16
+
+
 STAT_GS = 12  # channel granularity of the AdaGN statistics kept by the GEMM epilogue (C / 32 for C = 384)
 
 

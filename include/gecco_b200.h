@@ -82,6 +82,34 @@ typedef struct gecco_gemm_args {
 int gecco_gemm(const gecco_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Fused point-side MLP with residual (BroadcastingLayer.forward, models/set_transformer.py:165-166;
+ * MLP, models/mlp.py:5-39; GaussianActivation, models/activation.py:17-24):
+ *   out = res + W2 . g(W1_b . a + b1_b) + b2,   g(z) = (exp(-z^2 / (2 alpha^2)) - 0.7) / 0.28
+ * a:  bf16 [m, c] (the bf16 copy of the residual stream), W1_b: bf16 [hidden, c] per cloud
+ * (w1_rows_per_cloud = row offset between clouds, 0 = shared), b1_b fp32 [clouds][b1_stride];
+ * W2: bf16 [c, hidden], b2 fp32 [c].  The hidden activation stays on chip (TMEM -> shared memory).
+ * res / out_f32 (may alias), out_bf16, stats, rows_per_cloud, valid_rows as in gecco_gemm.
+ * Supported shapes: c == 384, hidden % 128 == 0, m % 256 == 0, rows_per_cloud % 256 == 0
+ * (GECCO_ERR_INVALID otherwise; the engine then runs the two projections through gecco_gemm).
+ * ------------------------------------------------------------------------ */
+typedef struct gecco_mlp_args {
+  const void* a;   int64_t lda;
+  const void* w1;  int64_t ldw1;  int32_t w1_rows_per_cloud;
+  const float* b1; int32_t b1_stride;
+  float act_alpha;
+  const void* w2;  int64_t ldw2;
+  const float* b2;
+  int32_t m, c, hidden;
+  int32_t rows_per_cloud, valid_rows;
+  const float* res; int64_t ldr;
+  float* out_f32;  int64_t ldo32;
+  void* out_bf16;  int64_t ldo16;
+  double* stats;
+} gecco_mlp_args;
+
+int gecco_mlp(const gecco_mlp_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
  * Group statistics: stats[cloud][c / group_size][{sum, sum of squares}] += over the
  * first valid_rows rows of each cloud (double accumulators, caller zeroes them).
  * The statistics half of nn.GroupNorm as used by AdaGN (models/normalization.py:21-25,37-38)

@@ -12,7 +12,8 @@ B, Np, K = 64, 2048, 384
 g = torch.Generator("cpu").manual_seed(0)
 a = torch.randn(B * Np, K, generator=g).to(dev).bfloat16()
 names = ["prod_total", "prod_wait_Afree", "prod_wait_Wfree", "mma_total", "mma_wait_acc", "mma_wait_A", "mma_wait_W", "tiles",
-         "epi0_total", "epi0_wait_acc", "epi1_total", "epi1_wait_acc", "mma_issue", "chunk_cycles", "chunks", "prefetch"]
+         "epi0_total", "epi0_wait_acc", "epi1_total", "epi1_wait_acc", "mma_issue", "chunk_cycles", "chunks", "prefetch",
+         "w0_tmem_ld_wait", "w0_res_wait", "w0_store_read_wait", "w0_stage_sts", "w0_stats"] + ["-"] * 8 + ["w0_fence", "w0_tma_store_issue"]
 import os
 SKIP = int(os.environ.get("EPI_SKIP", "0"))
 lib.gecco_set_option(ctypes.c_char_p(b"epi_skip"), SKIP)
@@ -44,5 +45,5 @@ for label, n_out, percloud, act, res in [("kvq", 1152, True, None, False), ("mlp
     d = dbg.cpu().double()
     lead, peer = d[0::2], d[1::2]
     print(f"== {label}: {us:.1f} us/launch, {2 * B * Np * n_out * K / us / 1e6:.0f} TFLOP/s")
-    print("   leader:", {n: int(lead[:, i].mean().item()) for i, n in enumerate(names)})
+    print("   leader:", {n: int(lead[:, i].mean().item()) for i, n in enumerate(names) if n != '-'})
     print("   peer  :", {n: int(peer[:, i].mean().item()) for i, n in enumerate(names) if i < 3 or i >= 8})
