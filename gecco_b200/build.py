@@ -39,7 +39,15 @@ def _newest_header() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    flags = list(NVCC_FLAGS)
+    marker = OBJ / ".debug_counters"
+    debug = os.environ.get("GECCO_DEBUG_COUNTERS", "0") == "1"
     OBJ.mkdir(parents=True, exist_ok=True)
+    if debug:
+        flags.append("-DGECCO_DEBUG_COUNTERS=1")
+    if debug != marker.exists():  # switching between the production and the instrumented build recompiles everything
+        force = True
+        marker.touch() if debug else marker.unlink()
     LIB.parent.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
     srcs = sorted(CSRC.glob("*.cu"))
@@ -54,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *flags, "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         return src, res
 

@@ -64,7 +64,7 @@ __device__ __forceinline__ void group_mean_rstd(const double* __restrict__ cstat
 // ------------------------------------------------------------------------------------------------
 // AdaGN apply (models/normalization.py:36-44): y = scale(t) * (x - mean_g) * rstd_g + bias(t)
 // with scale(t) = t . scale_w[c, :] + scale_b[c] (same for bias).  Padding rows are written as 0.
-constexpr int ADAGN_ROWS = 32;
+constexpr int ADAGN_ROWS = 8;  // rows per block: the inducer side has only 64 rows per cloud, small blocks fill the SMs
 
 __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, const double* __restrict__ stats,
                                    int stat_gs, const float* __restrict__ t, int t_stride, int ctx_dim,
@@ -75,18 +75,30 @@ __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, c
                                    long long ldo32) {
   const int cloud = blockIdx.y;
   const int r0 = blockIdx.x * ADAGN_ROWS;
-  const int r1 = min(r0 + ADAGN_ROWS, rows_per_cloud);
   const int gs = C / groups;
   const double count = static_cast<double>(valid_rows) * gs;
   const double* cstats = stats + (long long)cloud * (C / stat_gs) * 2;
   const long long row_base = (long long)cloud * rows_per_cloud;
   for (int cq = threadIdx.x; cq < C / 4; cq += blockDim.x) {
+    // the rows of this thread are loaded first: their latency overlaps the (double precision) statistics below
+    float4 xv[ADAGN_ROWS];
+#pragma unroll
+    for (int i = 0; i < ADAGN_ROWS; ++i) {
+      const int r = r0 + i;
+      xv[i] = (r < valid_rows && r < rows_per_cloud)
+                  ? __ldg(reinterpret_cast<const float4*>(x + (row_base + r) * ldx + cq * 4))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float a[4], s[4];
+    float mean = 0.f, rstd = 0.f;
+    int g_prev = -1;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = cq * 4 + j;
-      float mean, rstd;
-      group_mean_rstd(cstats, c / gs, gs, stat_gs, count, eps, mean, rstd);
+      if (c / gs != g_prev) {  // once per thread when the group size is a multiple of 4
+        g_prev = c / gs;
+        group_mean_rstd(cstats, g_prev, gs, stat_gs, count, eps, mean, rstd);
+      }
       float sc = __ldg(scale_b + c), bi = __ldg(bias_b + c);
       for (int i = 0; i < ctx_dim; ++i) {
         const float ti = __ldg(t + (long long)cloud * t_stride + i);
@@ -96,14 +108,16 @@ __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, c
       a[j] = sc * rstd;
       s[j] = bi - sc * rstd * mean;
     }
-    for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int i = 0; i < ADAGN_ROWS; ++i) {
+      const int r = r0 + i;
+      if (r >= rows_per_cloud) break;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < valid_rows) {
-        const float4 xv = *reinterpret_cast<const float4*>(x + (row_base + r) * ldx + cq * 4);
-        v.x = a[0] * xv.x + s[0];
-        v.y = a[1] * xv.y + s[1];
-        v.z = a[2] * xv.z + s[2];
-        v.w = a[3] * xv.w + s[3];
+        v.x = a[0] * xv[i].x + s[0];
+        v.y = a[1] * xv[i].y + s[1];
+        v.z = a[2] * xv[i].z + s[2];
+        v.w = a[3] * xv[i].w + s[3];
       }
       if (out16 != nullptr) {
         uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -120,7 +134,8 @@ __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, c
 //   Linear(AdaGN(x))[o] = sum_c (W[o,c] a[c]) x[c] + (b[o] + sum_c W[o,c] s[c])
 // so the consumer GEMM reads the bf16 residual stream directly with per-cloud weights.  grid (row blocks, clouds),
 // 256 threads; a warp owns whole output rows (coalesced fp32 reads, 8 B bf16 writes, shuffle-reduced bias dot).
-constexpr int FOLD_ROWS = 96;
+constexpr int FOLD_ROWS = 48;    // output rows per block
+constexpr int FOLD_CLOUDS = 4;   // clouds per block: every fp32 weight row is read once and folded for all of them
 constexpr int FOLD_MAXC = 1024;
 constexpr int FOLD_THREADS = 256;
 
@@ -129,46 +144,79 @@ fold_adagn_kernel(const float* __restrict__ W, long long ldw, const float* __res
                   const double* __restrict__ stats, int stat_gs, int groups, double count, float eps,
                   const float* __restrict__ t, int t_stride, const float* __restrict__ scale_w,
                   const float* __restrict__ scale_b, const float* __restrict__ bias_w, const float* __restrict__ bias_b,
-                  __nv_bfloat16* __restrict__ wf, long long ldwf, long long wf_cloud_stride, float* __restrict__ bf,
-                  int bf_stride) {
-  __shared__ __align__(16) float sa[FOLD_MAXC];
-  __shared__ __align__(16) float ss[FOLD_MAXC];
-  __shared__ float smean[128], srstd[128];
-  const int cloud = blockIdx.y;
+                  int clouds, __nv_bfloat16* __restrict__ wf, long long ldwf, long long wf_cloud_stride,
+                  float* __restrict__ bf, int bf_stride) {
+  extern __shared__ __align__(16) float fold_smem[];
+  float* sa = fold_smem;                      // [FOLD_CLOUDS][C]
+  float* ss = sa + FOLD_CLOUDS * C;           // [FOLD_CLOUDS][C]
+  float* smean = ss + FOLD_CLOUDS * C;        // [FOLD_CLOUDS][groups]
+  float* srstd = smean + FOLD_CLOUDS * groups;
+  const int cloud0 = blockIdx.y * FOLD_CLOUDS;
+  const int ncl = min(FOLD_CLOUDS, clouds - cloud0);
   const int gs = C / groups;
-  const double* cstats = stats + (long long)cloud * (C / stat_gs) * 2;
-  // group statistics once per group (the only double precision arithmetic), then per-channel coefficients in fp32
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  // group statistics once per (cloud, group) (the only double precision arithmetic), then per-channel coefficients
+  for (int i = threadIdx.x; i < ncl * groups; i += blockDim.x) {
+    const int cl = i / groups, g = i - cl * groups;
     float mean, rstd;
-    group_mean_rstd(cstats, g, gs, stat_gs, count, eps, mean, rstd);
-    smean[g] = mean;
-    srstd[g] = rstd;
+    group_mean_rstd(stats + (long long)(cloud0 + cl) * (C / stat_gs) * 2, g, gs, stat_gs, count, eps, mean, rstd);
+    smean[i] = mean;
+    srstd[i] = rstd;
   }
   __syncthreads();
-  const float tc = __ldg(t + (long long)cloud * t_stride);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int i = threadIdx.x; i < ncl * C; i += blockDim.x) {
+    const int cl = i / C, c = i - cl * C;
     const int g = c / gs;
+    const float tc = __ldg(t + (long long)(cloud0 + cl) * t_stride);
     const float sc = tc * __ldg(scale_w + c) + __ldg(scale_b + c);
     const float bi = tc * __ldg(bias_w + c) + __ldg(bias_b + c);
-    sa[c] = sc * srstd[g];
-    ss[c] = bi - sc * srstd[g] * smean[g];
+    const float a = sc * srstd[cl * groups + g];
+    sa[i] = a;
+    ss[i] = bi - a * smean[cl * groups + g];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o_end = min((int)(blockIdx.x + 1) * FOLD_ROWS, n_out);
-  for (int o = blockIdx.x * FOLD_ROWS + warp; o < o_end; o += FOLD_THREADS / 32) {
-    const float* wr = W + (long long)o * ldw;
-    __nv_bfloat16* dst = wf + (long long)cloud * wf_cloud_stride + (long long)o * ldwf;
-    float dot = 0.f;
+  constexpr int NW = FOLD_THREADS / 32;
+  constexpr int ILP = 2;  // weight rows in flight per warp
+  for (int ob = blockIdx.x * FOLD_ROWS + warp; ob < o_end; ob += NW * ILP) {
+    float dot[ILP][FOLD_CLOUDS];
+#pragma unroll
+    for (int u = 0; u < ILP; ++u)
+#pragma unroll
+      for (int cl = 0; cl < FOLD_CLOUDS; ++cl) dot[u][cl] = 0.f;
     for (int c = lane * 4; c < C; c += 128) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wr + c));
-      const float4 a = *reinterpret_cast<const float4*>(sa + c);
-      const float4 sv = *reinterpret_cast<const float4*>(ss + c);
-      dot += w.x * sv.x + w.y * sv.y + w.z * sv.z + w.w * sv.w;
-      *reinterpret_cast<uint2*>(dst + c) = make_uint2(pack_bf16x2(w.x * a.x, w.y * a.y), pack_bf16x2(w.z * a.z, w.w * a.w));
+      float4 w[ILP];
+#pragma unroll
+      for (int u = 0; u < ILP; ++u) {
+        const int o = ob + u * NW;
+        w[u] = o < o_end ? __ldg(reinterpret_cast<const float4*>(W + (long long)o * ldw + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int cl = 0; cl < FOLD_CLOUDS; ++cl) {
+        if (cl >= ncl) break;
+        const float4 a = *reinterpret_cast<const float4*>(sa + cl * C + c);
+        const float4 sv = *reinterpret_cast<const float4*>(ss + cl * C + c);
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+          const int o = ob + u * NW;
+          if (o < o_end) {
+            dot[u][cl] += w[u].x * sv.x + w[u].y * sv.y + w[u].z * sv.z + w[u].w * sv.w;
+            *reinterpret_cast<uint2*>(wf + (long long)(cloud0 + cl) * wf_cloud_stride + (long long)o * ldwf + c) =
+                make_uint2(pack_bf16x2(w[u].x * a.x, w[u].y * a.y), pack_bf16x2(w[u].z * a.z, w[u].w * a.w));
+          }
+        }
+      }
     }
-    dot = warp_sum(dot);
-    if (lane == 0) bf[(long long)cloud * bf_stride + o] = dot + (bias != nullptr ? __ldg(bias + o) : 0.f);
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      const int o = ob + u * NW;
+      const float b0 = (bias != nullptr && o < o_end) ? __ldg(bias + o) : 0.f;
+#pragma unroll
+      for (int cl = 0; cl < FOLD_CLOUDS; ++cl) {
+        const float d = warp_sum(dot[u][cl]);
+        if (lane == 0 && o < o_end && cl < ncl) bf[(long long)(cloud0 + cl) * bf_stride + o] = d + b0;
+      }
+    }
   }
 }
 
@@ -243,14 +291,51 @@ __global__ void lift_kernel(const float* __restrict__ xin, const float* __restri
 //   D = c_skip * xin + c_out * F              (diffusion.py:46-57)
 //   mode 2: Euler step, mode 3: Heun correction + churn of the next step (diffusion.py:317-347)
 constexpr int HEAD_WARPS = 8;
-constexpr int HEAD_MAX_PER_LANE = 32;  // C <= 1024
+constexpr int HEAD_ROWS_PER_WARP = 32;  // 256 rows per block: the per-block weight folding is amortised
+constexpr int HEAD_MAX_NQ = 8;  // C <= 1024
 
+// EDM preconditioning + sampler update of one output element (lanes 0..2 of the warp that owns the row).
+__device__ __forceinline__ void head_finish(const gecco_head_args& a, long long idx, float F, float c_skip, float c_out) {
+  if (a.mode == 0) {
+    a.out_f32[idx] = F;
+    return;
+  }
+  const float xi = a.xin[idx];
+  const float D = c_skip * xi + c_out * F;
+  if (a.mode == 1) {
+    a.out_f32[idx] = D;
+  } else if (a.mode == 2) {  // Euler
+    const double xh = a.x_hat[idx];
+    const double d_cur = (xh - static_cast<double>(D)) / a.t_hat;
+    const double xn = xh + (a.t_next - a.t_hat) * d_cur;
+    a.d_cur[idx] = d_cur;
+    a.x_next[idx] = xn;
+    a.xin_next[idx] = static_cast<float>(xn);
+  } else {  // Heun correction, then churn for the next step
+    const double xh = a.x_hat[idx];
+    const double xn = a.x_next[idx];
+    const double d_prime = (xn - static_cast<double>(D)) / a.t_next;
+    double xnew = xh + (a.t_next - a.t_hat) * (0.5 * a.d_cur[idx] + 0.5 * d_prime);
+    // the reference multiplies the 0-dim float64 churn factor into the fp32 noise tensor, which torch
+    // evaluates in fp32 (diffusion.py:325)
+    if (a.noise_next != nullptr)
+      xnew = xnew + static_cast<double>(__fmul_rn(static_cast<float>(a.churn_next), a.noise_next[idx]));
+    a.x_hat[idx] = xnew;
+    a.xin_next[idx] = static_cast<float>(xnew);
+  }
+}
+
+// NQ = C / 128 float4 per lane.  The normalisation is folded into the three weight rows once per block:
+//   GroupNorm:  F_o = sum_c x_c (r_c w_oc) - sum_c m_c r_c w_oc + b_o        (statistics per cloud)
+//   LayerNorm:  F_o = rstd (sum_c x_c w_oc - mean sum_c w_oc) + b_o          (statistics per row)
+// so a row costs NQ 16-byte loads, 12 NQ FMAs and three warp reductions; every warp keeps two rows in flight.
+template <int NQ>
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 head_kernel(const gecco_head_args a) {
   extern __shared__ float smem_head[];  // [groups][2] mean, rstd (GroupNorm mode)
   const int cloud = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = a.c;
+  constexpr int C = NQ * 128;
   const int gs = (a.norm == 2) ? C / a.groups : 1;
   if (a.norm == 2) {
     const double count = static_cast<double>(a.valid_rows) * gs;
@@ -268,70 +353,77 @@ head_kernel(const gecco_head_args a) {
   const float c_skip = sd * sd / (sg * sg + sd * sd);
   const float c_out = sg * sd / sqrtf(sg * sg + sd * sd);
 
-  const int nq = C / 128;  // float4 per lane
-  for (int r = blockIdx.x * HEAD_WARPS + warp; r < a.valid_rows; r += gridDim.x * HEAD_WARPS) {
-    const float* xr = a.x + ((long long)cloud * a.rows_per_cloud + r) * a.ldx;
-    float v[HEAD_MAX_PER_LANE];
-    for (int i = 0; i < nq; ++i) {
-      const float4 t4 = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-      v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
-    }
-    if (a.norm == 1) {  // LayerNorm over channels, no affine
-      float s = 0.f;
-      for (int i = 0; i < 4 * nq; ++i) s += v[i];
-      const float mean = warp_sum(s) / C;
-      float q = 0.f;
-      for (int i = 0; i < 4 * nq; ++i) { const float d = v[i] - mean; q += d * d; }
-      const float rstd = rsqrtf(warp_sum(q) / C + a.eps);
-      for (int i = 0; i < 4 * nq; ++i) v[i] = (v[i] - mean) * rstd;
-    } else if (a.norm == 2) {
-      for (int i = 0; i < nq; ++i)
+  // this lane's slice of the three (normalisation-folded) weight rows and the per-cloud constants
+  float4 w[3][NQ];
+  float kc[3];  // GroupNorm: sum_c m_c r_c w_oc;  LayerNorm: sum_c w_oc
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = i * 128 + lane * 4 + j;
-          const int g = c / gs;
-          v[4 * i + j] = (v[4 * i + j] - smem_head[g * 2]) * smem_head[g * 2 + 1];
-        }
-    }
-    float f[3];
+  for (int o = 0; o < 3; ++o) {
+    float acc = 0.f;
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      float acc = 0.f;
-      for (int i = 0; i < nq; ++i) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w_out + (long long)o * C + i * 128 + lane * 4));
-        acc += v[4 * i] * w4.x + v[4 * i + 1] * w4.y + v[4 * i + 2] * w4.z + v[4 * i + 3] * w4.w;
-      }
-      f[o] = warp_sum(acc) + __ldg(a.b_out + o);
-    }
-    if (lane < 3) {
-      const float F = lane == 0 ? f[0] : (lane == 1 ? f[1] : f[2]);
-      const long long idx = ((long long)cloud * a.valid_rows + r) * 3 + lane;
-      if (a.mode == 0) {
-        a.out_f32[idx] = F;
+    for (int i = 0; i < NQ; ++i) {
+      float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w_out + (long long)o * C + i * 128 + lane * 4));
+      if (a.norm == 2) {
+        const int c = i * 128 + lane * 4;
+        float m[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m[j] = smem_head[((c + j) / gs) * 2]; r[j] = smem_head[((c + j) / gs) * 2 + 1]; }
+        w4.x *= r[0]; w4.y *= r[1]; w4.z *= r[2]; w4.w *= r[3];
+        acc += m[0] * w4.x + m[1] * w4.y + m[2] * w4.z + m[3] * w4.w;
       } else {
-        const float xi = a.xin[idx];
-        const float D = c_skip * xi + c_out * F;
-        if (a.mode == 1) {
-          a.out_f32[idx] = D;
-        } else if (a.mode == 2) {  // Euler
-          const double xh = a.x_hat[idx];
-          const double d_cur = (xh - static_cast<double>(D)) / a.t_hat;
-          const double xn = xh + (a.t_next - a.t_hat) * d_cur;
-          a.d_cur[idx] = d_cur;
-          a.x_next[idx] = xn;
-          a.xin_next[idx] = static_cast<float>(xn);
-        } else {  // Heun correction, then churn for the next step
-          const double xh = a.x_hat[idx];
-          const double xn = a.x_next[idx];
-          const double d_prime = (xn - static_cast<double>(D)) / a.t_next;
-          double xnew = xh + (a.t_next - a.t_hat) * (0.5 * a.d_cur[idx] + 0.5 * d_prime);
-          // the reference multiplies the 0-dim float64 churn factor into the fp32 noise tensor, which torch
-          // evaluates in fp32 (diffusion.py:325)
-          if (a.noise_next != nullptr)
-            xnew = xnew + static_cast<double>(__fmul_rn(static_cast<float>(a.churn_next), a.noise_next[idx]));
-          a.x_hat[idx] = xnew;
-          a.xin_next[idx] = static_cast<float>(xnew);
+        acc += w4.x + w4.y + w4.z + w4.w;
+      }
+      w[o][i] = w4;
+    }
+    kc[o] = warp_sum(acc);
+  }
+  const float bo = lane < 3 ? __ldg(a.b_out + lane) : 0.f;
+
+  const int rb = (blockIdx.x * HEAD_WARPS + warp) * HEAD_ROWS_PER_WARP;
+  const float* xc = a.x + (long long)cloud * a.rows_per_cloud * a.ldx + lane * 4;
+#pragma unroll 1
+  for (int rr = 0; rr < HEAD_ROWS_PER_WARP; rr += 2) {
+    const int r0 = rb + rr;
+    if (r0 >= a.valid_rows) break;
+    const bool two = r0 + 1 < a.valid_rows;
+    float4 v[2][NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      v[0][i] = __ldg(reinterpret_cast<const float4*>(xc + (long long)r0 * a.ldx + i * 128));
+      v[1][i] = two ? __ldg(reinterpret_cast<const float4*>(xc + (long long)(r0 + 1) * a.ldx + i * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float f[3];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+          acc += v[u][i].x * w[o][i].x + v[u][i].y * w[o][i].y + v[u][i].z * w[o][i].z + v[u][i].w * w[o][i].w;
+        f[o] = warp_sum(acc);
+      }
+      if (a.norm == 1) {  // LayerNorm over channels, no affine: statistics of this row
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) s += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
+        const float mean = warp_sum(s) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float d0 = v[u][i].x - mean, d1 = v[u][i].y - mean, d2 = v[u][i].z - mean, d3 = v[u][i].w - mean;
+          q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
+        const float rstd = rsqrtf(warp_sum(q) / C + a.eps);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) f[o] = rstd * (f[o] - mean * kc[o]);
+      } else if (a.norm == 2) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) f[o] -= kc[o];
+      }
+      if (lane < 3) {
+        const float F = (lane == 0 ? f[0] : (lane == 1 ? f[1] : f[2])) + bo;
+        head_finish(a, ((long long)cloud * a.valid_rows + r0 + u) * 3 + lane, F, c_skip, c_out);
       }
     }
   }
@@ -448,10 +540,11 @@ int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s) {
   GECCO_REQUIRE(a.ctx_dim == 1, "fold_adagn: t_embed_dim must be 1");
   GECCO_REQUIRE(a.groups <= 128, "fold_adagn: at most 128 groups");
   if (a.n_out == 0 || a.clouds == 0) return GECCO_OK;
-  dim3 grid(ceil_div(a.n_out, FOLD_ROWS), a.clouds);
-  fold_adagn_kernel<<<grid, FOLD_THREADS, 0, s>>>(a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
+  dim3 grid(ceil_div(a.n_out, FOLD_ROWS), ceil_div(a.clouds, FOLD_CLOUDS));
+  const size_t smem = (size_t)FOLD_CLOUDS * (2 * a.c + 2 * a.groups) * sizeof(float);
+  fold_adagn_kernel<<<grid, FOLD_THREADS, smem, s>>>(a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
                                         (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b,
-                                        a.bias_w, a.bias_b, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf,
+                                        a.bias_w, a.bias_b, a.clouds, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf,
                                         a.wf_cloud_stride, a.bias_folded, a.bias_stride);
   GECCO_CHECK_LAUNCH("fold_adagn_kernel");
   return GECCO_OK;
@@ -472,7 +565,7 @@ int launch_lift(const gecco_lift_args& a, cudaStream_t s) {
 }
 
 int launch_head(const gecco_head_args& a, cudaStream_t s) {
-  GECCO_REQUIRE(a.c % 128 == 0 && a.c <= 128 * (HEAD_MAX_PER_LANE / 4), "head: C must be a multiple of 128 and <= 1024");
+  GECCO_REQUIRE(a.c % 128 == 0 && a.c <= 128 * HEAD_MAX_NQ, "head: C must be a multiple of 128 and <= 1024");
   GECCO_REQUIRE(a.ldx % 4 == 0, "head: ldx must be a multiple of 4");
   GECCO_REQUIRE(a.norm != 2 || (a.stats && a.groups > 0 && a.c % a.groups == 0 && (a.c / a.groups) % a.stat_gs == 0),
                 "head: GroupNorm needs statistics with a granularity dividing the group size");
@@ -480,11 +573,15 @@ int launch_head(const gecco_head_args& a, cudaStream_t s) {
   GECCO_REQUIRE(a.mode == 0 || (a.xin && a.sigma), "head: preconditioning needs xin and sigma");
   GECCO_REQUIRE(a.mode > 1 || a.out_f32, "head: no output");
   GECCO_REQUIRE(a.mode < 2 || (a.x_hat && a.x_next && a.d_cur && a.xin_next), "head: sampler state missing");
-  int gx = ceil_div(a.valid_rows, HEAD_WARPS);
-  if (gx > 1024) gx = 1024;
-  dim3 grid(gx, a.clouds);
+  dim3 grid(ceil_div(a.valid_rows, HEAD_WARPS * HEAD_ROWS_PER_WARP), a.clouds);
   const size_t sm = a.norm == 2 ? a.groups * 2 * sizeof(float) : 0;
-  head_kernel<<<grid, HEAD_WARPS * 32, sm, s>>>(a);
+  switch (a.c / 128) {
+#define GECCO_HEAD_CASE(NQ) case NQ: head_kernel<NQ><<<grid, HEAD_WARPS * 32, sm, s>>>(a); break;
+    GECCO_HEAD_CASE(1) GECCO_HEAD_CASE(2) GECCO_HEAD_CASE(3) GECCO_HEAD_CASE(4)
+    GECCO_HEAD_CASE(5) GECCO_HEAD_CASE(6) GECCO_HEAD_CASE(7) GECCO_HEAD_CASE(8)
+#undef GECCO_HEAD_CASE
+    default: GECCO_REQUIRE(false, "head: C must be a multiple of 128 and <= 1024");
+  }
   GECCO_CHECK_LAUNCH("head_kernel");
   return GECCO_OK;
 }

@@ -1,12 +1,14 @@
 // Row-tile epilogue shared by the tcgen05 kernels: drains a 128-row x 192-column fp32 accumulator panel from
 // TMEM in 32-column chunks and applies, in this order,
 //   + bias[cloud][n]  + xyz embed  -> Gaussian activation -> + residual -> AdaGN statistics -> fp32 / bf16 stores.
-// The TMEM layout gives every thread one ROW of the tile; global memory wants whole rows segments per warp
-// instruction.  Inputs: the fp32 residual chunk is prefetched by TMA into swizzled shared memory by a loader thread
-// (res_full / res_empty mbarriers, one buffer per group).  Outputs: every warp transposes its own 32 x 32 chunk
-// through a private swizzled staging area (only __syncwarp, no block barrier, no bulk-store latency) and writes it
-// with coalesced 16 B stores: 4 rows x 128 B (fp32) or 8 rows x 64 B (bf16) per instruction, full sectors only.
-// Two epilogue groups of 128 threads (4 warps each, warp q <-> TMEM lanes 32q..) work on alternate chunks.
+// The TMEM layout gives every thread one ROW of the tile; global memory wants whole row segments per request, so all
+// global traffic of the epilogue goes through TMA and swizzled shared memory.
+// Two epilogue groups of 128 threads (4 warps each, warp q <-> TMEM lanes 32q..) work on alternate chunks.  Each group
+// owns "X" buffers of 128 rows x 32 fp32 columns (16 KB, SWIZZLE_128B): the loader thread TMA-loads the fp32 residual
+// chunk into one, every thread adds its accumulator row IN PLACE, and each warp bulk-stores its 32 x 32 block straight
+// from the same buffer (res_full / res_empty mbarriers).  With a residual a group has two X buffers, so the residual
+// of chunk i+1 is in flight while chunk i is processed and chunk i-1's store drains; without a residual one buffer
+// serves as plain output staging.  The bf16 copy goes through a per-warp 2 KB staging area (SWIZZLE_64B).
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -19,10 +21,10 @@ constexpr int EPI_THREADS = 128;                      // per group
 constexpr int EPI_GROUPS = 2;
 constexpr int EPI_CHUNK = 32;                         // columns per chunk
 constexpr int EPI_PANEL = 192;                        // columns per panel (16 AdaGN groups of 12)
-constexpr int EPI_RES_BYTES = 128 * EPI_CHUNK * 4;    // one fp32 chunk (TMA box {32, 128}, SWIZZLE_128B)
+constexpr int EPI_RES_BYTES = 128 * EPI_CHUNK * 4;    // one fp32 chunk (TMA box {32, 128}, SWIZZLE_128B): an X buffer
 constexpr int EPI_O16_BYTES = 128 * EPI_CHUNK * 2;    // one bf16 chunk (TMA box {32, 128}, SWIZZLE_64B)
 constexpr int EPI_BIAS_BYTES = 8 * 384;                // per-warp bias staging (3 chunks x 32 floats)
-constexpr int EPI_SMEM_BYTES = 4 * EPI_RES_BYTES + 2 * EPI_O16_BYTES + EPI_BIAS_BYTES;  // res[2] | o32 | o16 | bias
+constexpr int EPI_NUM_BARS = 4 * EPI_GROUPS;          // res_full[group][2] | res_empty[group][2]
 
 struct EpiParams {
   int M, n_out;
@@ -45,43 +47,55 @@ struct EpiParams {
 };
 
 struct EpiSmem {
-  uint8_t* res;  // [group] x EPI_RES_BYTES, 1024 B aligned
-  uint8_t* o32;  // [group][warp] x 4 KB fp32 staging (32 rows x 128 B, 128 B swizzle)
+  uint8_t* x0;   // [group] x EPI_RES_BYTES, 1024 B aligned: X buffer 0 of every group
+  uint8_t* x1;   // [group] x EPI_RES_BYTES: X buffer 1 (only with a residual)
   uint8_t* o16;  // [group][warp] x 2 KB bf16 staging (32 rows x 64 B, 64 B swizzle)
   uint8_t* bias; // [group][warp] x 384 B
-  uint64_t* res_full;   // [group], count 1 + tx
-  uint64_t* res_empty;  // [group], count EPI_THREADS
+  uint64_t* res_full;   // [group][2], count 1 + tx
+  uint64_t* res_empty;  // [group][2], count 4 (one arrival per warp of the group)
 };
 
 // Shared memory the epilogue needs for a given output configuration (1024 B aligned pieces), and its carving.
 __host__ __device__ inline int epi_smem_bytes(bool has_res, bool has_o32, bool has_o16) {
-  return (has_res ? EPI_GROUPS * EPI_RES_BYTES : 0) + (has_o32 ? EPI_GROUPS * EPI_RES_BYTES : 0) +
-         (has_o16 ? EPI_GROUPS * EPI_O16_BYTES : 0) + EPI_BIAS_BYTES;
+  return (has_res ? 2 : (has_o32 ? 1 : 0)) * EPI_GROUPS * EPI_RES_BYTES + (has_o16 ? EPI_GROUPS * EPI_O16_BYTES : 0) +
+         EPI_BIAS_BYTES;
 }
 // Returns the first byte after the epilogue's area.
 __device__ __forceinline__ uint8_t* epi_smem_carve(EpiSmem& es, uint8_t* base, bool has_res, bool has_o32, bool has_o16) {
-  es.res = base;
+  es.x0 = base;
+  if (has_res || has_o32) base += EPI_GROUPS * EPI_RES_BYTES;
+  es.x1 = base;
   if (has_res) base += EPI_GROUPS * EPI_RES_BYTES;
-  es.o32 = base;
-  if (has_o32) base += EPI_GROUPS * EPI_RES_BYTES;
   es.o16 = base;
   if (has_o16) base += EPI_GROUPS * EPI_O16_BYTES;
   es.bias = base;
   return base + EPI_BIAS_BYTES;
 }
+// One thread, before the block-wide (or cluster-wide) barrier that publishes the mbarriers.
+__device__ __forceinline__ void epi_bar_init(const EpiSmem& es) {
+  for (int i = 0; i < 2 * EPI_GROUPS; ++i) {
+    mbar_init(&es.res_full[i], 1);
+    mbar_init(&es.res_empty[i], EPI_THREADS / 32);
+  }
+}
 
-// Loader side (one thread): prefetches the residual chunks of one panel in the order the epilogue consumes them.
+// Loader side (one thread): the residual chunk at column col0 for group g; cnt = chunks loaded for that group so far.
+__device__ __forceinline__ void epi_load_residual_chunk(const EpiSmem& sm, const CUtensorMap* tma_res, int m0, int col0,
+                                                        int g, uint32_t& cnt) {
+  const uint32_t b = cnt & 1u, phase = (cnt >> 1) & 1u;
+  mbar_wait(&sm.res_empty[g * 2 + b], phase ^ 1u);
+  mbar_arrive_expect_tx(&sm.res_full[g * 2 + b], EPI_RES_BYTES);
+  tma_load_2d((b ? sm.x1 : sm.x0) + g * EPI_RES_BYTES, tma_res, &sm.res_full[g * 2 + b], col0, m0);
+  ++cnt;
+}
+// The residual chunks of one panel in the order the epilogue consumes them (chunk c belongs to group c & 1).
 __device__ __forceinline__ void epi_load_residual_panel(const EpiParams& p, const EpiSmem& sm, const CUtensorMap* tma_res,
                                                         int m0, int n0, uint32_t (&cnt)[EPI_GROUPS]) {
 #pragma unroll 1
   for (int c = 0; c < EPI_PANEL / EPI_CHUNK; ++c) {
     const int col0 = n0 + c * EPI_CHUNK;
     if (col0 >= p.n_out) break;
-    const uint32_t buf = c & 1u, phase = cnt[buf] & 1u;  // chunk c belongs to group c & 1
-    mbar_wait(&sm.res_empty[buf], phase ^ 1u);
-    mbar_arrive_expect_tx(&sm.res_full[buf], EPI_RES_BYTES);
-    tma_load_2d(sm.res + buf * EPI_RES_BYTES, tma_res, &sm.res_full[buf], col0, m0);
-    ++cnt[buf];
+    epi_load_residual_chunk(sm, tma_res, m0, col0, c & 1, cnt[c & 1]);
   }
 }
 
@@ -143,12 +157,11 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
 struct EpiThread {
   int grp, q, lane;
   uint32_t x7;          // (lane & 7) << 4: 128 B swizzle term of row `lane` (and of tile row q*32+lane)
-  uint32_t w32;         // fp32 staging, write side: piece j of row `lane` at  w32 | ((j << 4) ^ x7)
-  uint32_t r32e, r32o;  // fp32 staging, read side: rows 4i + lane/8, piece lane%8: (i even ? r32e : r32o) + i * 512
+  uint32_t xw0;         // X buffer 0, this thread's row (q*32+lane of the group's 128): piece j at  xw | ((j << 4) ^ x7)
+  uint32_t xs0;         // X buffer 0, this warp's 32 rows (source of the fp32 bulk store)
+  uint32_t xdelta;      // X buffer 1 = X buffer 0 + xdelta (multiple of 1024 B)
   uint32_t x3, w16;     // bf16 staging, write side: piece j of row `lane` at  w16 | ((j << 4) ^ x3)
-  uint32_t r16;         // bf16 staging, read side: rows 8i + lane/4, piece lane%4: r16 + i * 512
-  uint32_t s32, s16;    // bases of this warp's staging areas (sources of the bulk stores)
-  uint32_t res;         // residual chunk of this group, row q*32+lane: piece j at  res | ((j << 4) ^ x7)
+  uint32_t s16;         // base of this warp's bf16 staging area (source of the bf16 bulk store)
   uint32_t bias;        // per-warp bias staging: 3 chunks x 32 floats
 };
 
@@ -157,18 +170,13 @@ __device__ __forceinline__ EpiThread epi_thread_init(const EpiSmem& sm, int grp,
   t.grp = grp; t.q = tid >> 5; t.lane = tid & 31;
   const uint32_t lane = t.lane, w = grp * 4 + t.q;
   t.x7 = (lane & 7u) << 4;
-  const uint32_t s32 = smem_u32(sm.o32) + w * 4096u;
-  t.w32 = s32 + lane * 128u;
-  t.s32 = s32;
-  const uint32_t rr = lane >> 3, jj = lane & 7u;
-  t.r32e = s32 + rr * 128u + ((jj ^ rr) << 4);
-  t.r32o = s32 + rr * 128u + ((jj ^ (rr + 4u)) << 4);
+  t.xs0 = smem_u32(sm.x0) + grp * EPI_RES_BYTES + t.q * 4096u;
+  t.xw0 = t.xs0 + lane * 128u;
+  t.xdelta = smem_u32(sm.x1) - smem_u32(sm.x0);
   t.x3 = ((lane >> 1) & 3u) << 4;
   const uint32_t s16 = smem_u32(sm.o16) + w * 2048u;
   t.w16 = s16 + lane * 64u;
   t.s16 = s16;
-  t.r16 = s16 + (lane >> 2) * 64u + (((lane & 3u) ^ ((lane >> 3) & 3u)) << 4);
-  t.res = smem_u32(sm.res) + grp * EPI_RES_BYTES + (t.q * 32u + lane) * 128u;
   t.bias = smem_u32(sm.bias) + w * 384u;
   return t;
 }
@@ -189,7 +197,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiThread
 
 #define EPI_TIMED(slot, stmt)                                                        \
   do {                                                                              \
-    if (p.dbg != nullptr) {                                                         \
+    if (GECCO_DBG_ON(p.dbg)) {                                                         \
       const long long t0__ = clock64();                                             \
       stmt;                                                                         \
       if (t.lane == 0 && t.q == 0 && t.grp == 0) p.dbg[(long long)blockIdx.x * 32 + (slot)] += clock64() - t0__; \
@@ -223,20 +231,26 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
 #pragma unroll
     for (int j = 0; j < EPI_CHUNK; ++j) v[j] = fmaf(ex2_approx(v[j] * v[j] * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
   }
-  if (p.has_res && !(p.skip & 2)) {
-    EPI_TIMED(17, mbar_wait(&sm.res_full[t.grp], cnt & 1u));
+  // The previous chunk's bulk stores have finished reading their staging (its X buffer and the bf16 area): with a
+  // residual that X buffer goes back to the loader, which refills it while this chunk is processed.
+  const bool use_res = p.has_res && !(p.skip & 2);
+  const uint32_t b = use_res ? (cnt & 1u) : 0u;
+  const uint32_t xw = t.xw0 + b * t.xdelta, xs = t.xs0 + b * t.xdelta;
+  EPI_TIMED(18, { if (t.lane == 0) tma_store_wait_read<0>(); __syncwarp(); });
+  if (use_res) {
+    if (t.lane == 0 && cnt > 0) mbar_arrive(&sm.res_empty[t.grp * 2 + (b ^ 1u)]);
+    EPI_TIMED(17, mbar_wait(&sm.res_full[t.grp * 2 + b], (cnt >> 1) & 1u));
 #pragma unroll
     for (int h = 0; h < 2; ++h) {  // two batches of four loads: latency overlapped, bounded register use
       float4 x[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = lds128(t.res | (((4 * h + j) << 4) ^ t.x7));
+      for (int j = 0; j < 4; ++j) x[j] = lds128(xw | (((4 * h + j) << 4) ^ t.x7));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         v[16 * h + 4 * j + 0] += x[j].x; v[16 * h + 4 * j + 1] += x[j].y;
         v[16 * h + 4 * j + 2] += x[j].z; v[16 * h + 4 * j + 3] += x[j].w;
       }
     }
-    mbar_arrive(&sm.res_empty[t.grp]);
   }
   if (!rows_valid && !row_valid) {
 #pragma unroll
@@ -251,14 +265,14 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
       st[2 * g + 1] = fmaf(v[j], v[j], st[2 * g + 1]);
     }
   }
-  // stage this warp's 32 x 32 block in its private swizzled area and hand it to TMA: one bulk tensor store per
-  // output (box {32 columns, 32 rows}; rows / columns outside the matrix are clipped by the tensor map)
-  EPI_TIMED(18, { if (t.lane == 0) tma_store_wait_read<0>(); __syncwarp(); });  // previous chunk's stores have read the staging area
+  // this thread's row goes back into the X buffer (over its own residual values), the warp's 32 x 32 block is then
+  // bulk-stored from there: one tensor store per output (box {32 columns, 32 rows}; rows / columns outside the
+  // matrix are clipped by the tensor map)
   long long tf0__ = 0;
-  if (p.dbg != nullptr) tf0__ = clock64();
+  if (GECCO_DBG_ON(p.dbg)) tf0__ = clock64();
   if (p.o32 != nullptr) {
 #pragma unroll
-    for (int j = 0; j < EPI_CHUNK / 4; ++j) sts128(t.w32 | ((j << 4) ^ t.x7), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < EPI_CHUNK / 4; ++j) sts128(xw | ((j << 4) ^ t.x7), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
   if (p.o16 != nullptr) {
 #pragma unroll
@@ -267,16 +281,16 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
   }
   long long tf1__ = 0, tf2__ = 0;
-  if (p.dbg != nullptr) tf1__ = clock64();
+  if (GECCO_DBG_ON(p.dbg)) tf1__ = clock64();
   if (!(p.skip & 4)) fence_proxy_async_smem();
   __syncwarp();
-  if (p.dbg != nullptr) tf2__ = clock64();
+  if (GECCO_DBG_ON(p.dbg)) tf2__ = clock64();
   if (t.lane == 0 && !(p.skip & 1)) {
-    if (p.o32 != nullptr) tma_store_2d_addr(tma_o32, t.s32, col0, m0 + t.q * 32);
+    if (p.o32 != nullptr) tma_store_2d_addr(tma_o32, xs, col0, m0 + t.q * 32);
     if (p.o16 != nullptr) tma_store_2d_addr(tma_o16, t.s16, col0, m0 + t.q * 32);
     tma_store_commit();
   }
-  if (p.dbg != nullptr && t.lane == 0 && t.q == 0 && t.grp == 0) {
+  if (GECCO_DBG_ON(p.dbg) && t.lane == 0 && t.q == 0 && t.grp == 0) {
     const long long tf3__ = clock64();
     p.dbg[(long long)blockIdx.x * 32 + 19] += tf1__ - tf0__;
     p.dbg[(long long)blockIdx.x * 32 + 29] += tf2__ - tf1__;
@@ -349,12 +363,12 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
   step(std::integral_constant<int, 2>{});
   if constexpr (kStats) {
     long long ts0__ = 0;
-    if (p.dbg != nullptr) ts0__ = clock64();
+    if (GECCO_DBG_ON(p.dbg)) ts0__ = clock64();
     const float mine = warp_reduce_scatter32(st, t.lane);
     const int gidx = (n0 / 12) * 2 + t.lane;  // [group][{sum, sumsq}]
     if (gidx < (p.n_out / 12) * 2 && m0 + t.q * 32 < p.M)
       if (!(p.skip & 8)) atomicAdd(p.stats + (long long)cloud * (p.n_out / 12) * 2 + gidx, static_cast<double>(mine));
-    if (p.dbg != nullptr && t.lane == 0 && t.q == 0 && t.grp == 0) p.dbg[(long long)blockIdx.x * 32 + 20] += clock64() - ts0__;
+    if (GECCO_DBG_ON(p.dbg) && t.lane == 0 && t.q == 0 && t.grp == 0) p.dbg[(long long)blockIdx.x * 32 + 20] += clock64() - ts0__;
   }
 }
 

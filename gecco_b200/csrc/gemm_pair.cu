@@ -50,7 +50,7 @@ __device__ __forceinline__ int num_kb_of(const PParams& p) { return p.num_kb; }
 // cycles spent in a barrier wait, accumulated into `acc` when the debug buffer is set
 #define TIMED_WAIT(acc, bar, parity)        \
   do {                                      \
-    if (p.dbg != nullptr) {                 \
+    if (GECCO_DBG_ON(p.dbg)) {                 \
       const long long t0__ = clock64();     \
       mbar_wait(bar, parity);               \
       acc += clock64() - t0__;              \
@@ -81,9 +81,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* b_empty = b_full + MAX_BSTAGES;   // [MAX_BSTAGES]  each CTA
   uint64_t* acc_full = b_empty + MAX_BSTAGES; // [2]        each CTA
   uint64_t* acc_empty = acc_full + 2;         // [2]        leader: one arrival per epilogue warp of both CTAs
-  es.res_full = acc_empty + 2;   // [2]
-  es.res_empty = acc_empty + 4;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 6);
+  es.res_full = acc_empty + 2;   // [EPI_GROUPS][2]
+  es.res_empty = es.res_full + EPI_NUM_BARS / 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_full + EPI_NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,9 +111,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 2 * EPI_GROUPS * EPI_THREADS / 32);
-      mbar_init(&es.res_full[i], 1);
-      mbar_init(&es.res_empty[i], EPI_THREADS);
     }
+    epi_bar_init(es);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -157,7 +156,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
-    if (p.dbg != nullptr) {
+    if (GECCO_DBG_ON(p.dbg)) {
       long long* d = p.dbg + (long long)blockIdx.x * 32;
       d[0] = clock64() - t_start; d[1] = w_aempty; d[2] = w_bempty;
     }
@@ -186,11 +185,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * A_KB_BYTES));
               const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * stage_bytes + kk * B_STAGE_BYTES));
               long long ti0 = 0;
-              if (p.dbg != nullptr) ti0 = clock64();
+              if (GECCO_DBG_ON(p.dbg)) ti0 = clock64();
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
               if (last_nb) umma_commit_pair(&a_empty[kb]);  // the k-block may be reloaded for the next row block
-              if (p.dbg != nullptr) w_issue += clock64() - ti0;
+              if (GECCO_DBG_ON(p.dbg)) w_issue += clock64() - ti0;
             }
             umma_commit_pair(&b_empty[stage]);
             if (++stage == BSTAGES) { stage = 0; bphase ^= 1u; }
@@ -198,7 +197,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           umma_commit_pair(&acc_full[slot]);
         }
       }
-      if (p.dbg != nullptr) {
+      if (GECCO_DBG_ON(p.dbg)) {
         long long* d = p.dbg + (long long)blockIdx.x * 32;
         d[3] = clock64() - t_start; d[4] = w_acc; d[5] = w_afull; d[6] = w_bfull; d[7] = tile; d[12] = w_issue;
       }
@@ -226,9 +225,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int nb = 0; nb < p.num_n_blocks; ++nb, ++tile) {
         const uint32_t slot = tile & 1u;
         long long tp0 = 0;
-        if (p.dbg != nullptr) tp0 = clock64();
+        if (GECCO_DBG_ON(p.dbg)) tp0 = clock64();
         epi_prefetch(p.e, et, m0, nb * BN);
-        if (p.dbg != nullptr) w_pref += clock64() - tp0;
+        if (GECCO_DBG_ON(p.dbg)) w_pref += clock64() - tp0;
         TIMED_WAIT(w_accfull, &acc_full[slot], (tile >> 1) & 1u);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * ACC_COLS;
@@ -239,7 +238,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
     if (et.lane == 0) tma_store_wait_read<0>();
-    if (p.dbg != nullptr && et.lane == 0 && et.q == 0) {
+    if (GECCO_DBG_ON(p.dbg) && et.lane == 0 && et.q == 0) {
       long long* d = p.dbg + (long long)blockIdx.x * 32 + 8 + 2 * et.grp;
       d[0] = clock64() - t_start; d[1] = w_accfull;
       if (et.grp == 0) p.dbg[(long long)blockIdx.x * 32 + 15] = w_pref;

@@ -58,9 +58,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* empty_bar = bars + MAX_STAGES;   // [MAX_STAGES]
   uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [2]
   uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2;  // [2]  one arrival per epilogue warp
-  es.res_full = bars + 2 * MAX_STAGES + 4;   // [2]
-  es.res_empty = bars + 2 * MAX_STAGES + 6;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
+  es.res_full = bars + 2 * MAX_STAGES + 4;   // [EPI_GROUPS][2]
+  es.res_empty = es.res_full + EPI_NUM_BARS / 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_full + EPI_NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,9 +82,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], EPI_GROUPS * EPI_THREADS / 32);
-      mbar_init(&es.res_full[i], 1);
-      mbar_init(&es.res_empty[i], EPI_THREADS);
     }
+    epi_bar_init(es);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);

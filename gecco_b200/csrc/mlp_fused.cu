@@ -36,7 +36,7 @@ namespace {
 // cycles spent in `stmt`, accumulated into `acc` when the debug buffer is set
 #define TIMED(acc, stmt)                    \
   do {                                      \
-    if (p.dbg != nullptr) {                 \
+    if (GECCO_DBG_ON(p.dbg)) {                 \
       const long long t0__ = clock64();     \
       stmt;                                 \
       acc += clock64() - t0__;              \
@@ -64,7 +64,8 @@ constexpr int THREADS = 128 + EPI_GROUPS * EPI_THREADS;
 constexpr int EPI_WARPS = EPI_GROUPS * EPI_THREADS / 32;  // 8
 constexpr int SMEM_BYTES = 1024 /*align*/ + NKB * A_KB_BYTES + HKB * H_KB_BYTES + W1_SLOTS * W1_SLOT + W2_SLOTS * W2_SLOT +
                            EPI_GROUPS * EPI_RES_BYTES + EPI_BIAS_BYTES + 512 /*barriers*/;
-static_assert(HKB * H_KB_BYTES == EPI_GROUPS * EPI_RES_BYTES, "the fp32 output staging aliases the hidden chunk buffer");
+static_assert(HKB * H_KB_BYTES == EPI_GROUPS * EPI_RES_BYTES, "the second residual / output buffers alias the hidden chunk buffer");
+static_assert((C / EPI_CHUNK / EPI_GROUPS) % 2 == 0, "every group must start a row block on its first buffer");
 static_assert(W2_SLOTS * W2_SLOT >= EPI_GROUPS * EPI_O16_BYTES, "the bf16 output staging aliases the W2 ring");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -96,8 +97,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint8_t* sW2 = sW1 + W1_SLOTS * W1_SLOT;          // [W2_SLOTS] | bf16 output staging of the epilogue
   uint8_t* sE = sW2 + W2_SLOTS * W2_SLOT;
   EpiSmem es;
-  es.res = sE;
-  es.o32 = sH;
+  es.x0 = sE;    // residual / fp32 output staging, first buffer of each group: dedicated, so the loader can run ahead
+  es.x1 = sH;    // second buffer of each group: the hidden chunk buffer, free once Y is complete
   es.o16 = sW2;
   es.bias = sE + EPI_GROUPS * EPI_RES_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(es.bias + EPI_BIAS_BYTES);
@@ -114,9 +115,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* y_full = hc_empty + 1;               // [1] each CTA
   uint64_t* y_empty = y_full + 1;                // [1] leader: one arrival per epilogue warp of both CTAs
   uint64_t* epi_done = y_empty + 1;              // [1] each CTA: output staging (hidden chunk buffer, W2 ring) is free again
-  es.res_full = epi_done + 1;                    // [2]
-  es.res_empty = es.res_full + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_empty + 2);
+  es.res_full = epi_done + 1;                    // [EPI_GROUPS][2]
+  es.res_empty = es.res_full + EPI_NUM_BARS / 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_full + EPI_NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,10 +146,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     mbar_init(y_full, 1);
     mbar_init(y_empty, 2 * EPI_WARPS);
     mbar_init(epi_done, EPI_WARPS);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&es.res_full[i], 1);
-      mbar_init(&es.res_empty[i], EPI_THREADS);
-    }
+    epi_bar_init(es);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -184,7 +182,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
       }
-      if (p.dbg != nullptr) {
+      if (GECCO_DBG_ON(p.dbg)) {
         long long* d = p.dbg + (long long)blockIdx.x * 32;
         d[0] = clock64() - t_start; d[1] = c_a; d[2] = c_w1;
       }
@@ -205,7 +203,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
       }
-      if (p.dbg != nullptr) p.dbg[(long long)blockIdx.x * 32 + 3] = c_w2;
+      if (GECCO_DBG_ON(p.dbg)) p.dbg[(long long)blockIdx.x * 32 + 3] = c_w2;
     } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------------------ MMA issuer (leader CTA)
       if (rank == 0) {
@@ -264,7 +262,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           umma_commit_pair(hc_empty);
           if (j == (uint32_t)nch - 1) umma_commit_pair(y_full);
         }
-        if (p.dbg != nullptr) {
+        if (GECCO_DBG_ON(p.dbg)) {
           long long* d = p.dbg + (long long)blockIdx.x * 32;
           d[4] = clock64() - t_start; d[5] = c_w1f; d[6] = c_af; d[7] = c_hr; d[8] = c_ye; d[9] = c_w2f; d[21] = c_hf;
         }
@@ -273,9 +271,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       // ------------------------------------------------------------ residual loader
       if (p.e.has_res && !(p.e.skip & 2)) {
         uint32_t cnt[EPI_GROUPS] = {0, 0};
-        for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs) {
+        uint32_t it = 0;
+        for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs, ++it) {
           const int m0 = pb * 2 * BM + (int)rank * BM;
-          for (int n0 = 0; n0 < C; n0 += EPI_PANEL) epi_load_residual_panel(p.e, es, &tma_res, m0, n0, cnt);
+          // every group starts a row block on its dedicated buffer: the first chunk of each group is loaded ahead of the
+          // epilogue; the second buffers alias the hidden chunk, which the second GEMM reads until Y is complete
+          epi_load_residual_chunk(es, &tma_res, m0, 0, 0, cnt[0]);
+          epi_load_residual_chunk(es, &tma_res, m0, EPI_CHUNK, 1, cnt[1]);
+          mbar_wait(y_full, it & 1u);
+          for (int c = 2; c < C / EPI_CHUNK; ++c) epi_load_residual_chunk(es, &tma_res, m0, c * EPI_CHUNK, c & 1, cnt[c & 1]);
         }
       }
     }
@@ -300,7 +304,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         TIMED(c_hf, mbar_wait(h_full, g & 1u));
         tc_fence_after_sync();
         long long tl0 = 0;
-        if (p.dbg != nullptr) tl0 = clock64();
+        if (GECCO_DBG_ON(p.dbg)) tl0 = clock64();
         uint32_t r0[32], r1[32];
         tmem_ld32_issue(tmem_h, r0);
         tmem_ld32_issue(tmem_h + 32, r1);
@@ -310,7 +314,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(h_free);
-        if (p.dbg != nullptr) c_ld += clock64() - tl0;
+        if (GECCO_DBG_ON(p.dbg)) c_ld += clock64() - tl0;
         const float4* bp = reinterpret_cast<const float4*>(b1 + j * HC);
         uint32_t pk[32];
 #pragma unroll
@@ -329,7 +333,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           pk[16 + 2 * i + 1] = pack_bf16x2(gauss_act(__uint_as_float(r1[4 * i + 2]) + bi.z, p.act_k),
                                            gauss_act(__uint_as_float(r1[4 * i + 3]) + bi.w, p.act_k));
         }
-        if (p.dbg != nullptr) c_act += clock64() - tl0;
+        if (GECCO_DBG_ON(p.dbg)) c_act += clock64() - tl0;
         // the second GEMM of the previous chunk has finished reading the shared-memory chunk
         TIMED(c_hce, mbar_wait(hc_empty, (g & 1u) ^ 1u));
 #pragma unroll
@@ -344,7 +348,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       TIMED(c_yf, mbar_wait(y_full, it & 1u));
       tc_fence_after_sync();
       long long t_epi = 0;
-      if (p.dbg != nullptr) t_epi = clock64();
+      if (GECCO_DBG_ON(p.dbg)) t_epi = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       epi_panel<kStats>(p.e, es, et, &tma_o32, &tma_o16, taddr, m0, 0, cnt);
       __syncwarp();
@@ -358,9 +362,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_arrive(epi_done);
       }
       named_bar_sync(1, EPI_GROUPS * EPI_THREADS);
-      if (p.dbg != nullptr) c_epi += clock64() - t_epi;
+      if (GECCO_DBG_ON(p.dbg)) c_epi += clock64() - t_epi;
     }
-    if (p.dbg != nullptr && lane == 0 && ew == 0) {
+    if (GECCO_DBG_ON(p.dbg) && lane == 0 && ew == 0) {
       long long* d = p.dbg + (long long)blockIdx.x * 32;
       d[10] = clock64() - t_start; d[11] = c_hf; d[12] = c_hce; d[13] = c_yf; d[14] = c_epi; d[25] = c_ld; d[26] = c_act;
     }

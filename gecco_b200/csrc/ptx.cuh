@@ -7,6 +7,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Cycle-counter instrumentation of the tcgen05 kernels (gecco_set_debug_buffer) is compiled in only when the library
+// is built with GECCO_DEBUG_COUNTERS=1 (gecco_b200/build.py): the counters cost registers in the 40-register role warps.
+#ifdef GECCO_DEBUG_COUNTERS
+#define GECCO_DBG_ON(ptr) ((ptr) != nullptr)
+#else
+#define GECCO_DBG_ON(ptr) (false)
+#endif
+
 namespace gecco {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
