@@ -181,18 +181,32 @@ __device__ __forceinline__ EpiThread epi_thread_init(const EpiSmem& sm, int grp,
   return t;
 }
 
-// Before the accumulator is waited for: stage the bias of this group's three chunks (latency overlaps the wait).
-__device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiThread& t, int m0, int n0) {
+// Bias of this group's three chunks of panel (m0, n0): loaded into registers one panel AHEAD (the global-load latency
+// overlaps the whole previous panel), staged into the warp's shared-memory area right before the panel is drained.
+struct EpiBias { float b[3]; };
+__device__ __forceinline__ void epi_bias_load(const EpiParams& p, const EpiThread& t, int m0, int n0, EpiBias& r) {
+  r.b[0] = r.b[1] = r.b[2] = 0.f;
   if (p.bias == nullptr) return;
   const int cloud = (m0 + t.q * 32) / p.rows_per_cloud;
   const float* bp = p.bias + (long long)cloud * p.bias_stride + n0 + t.grp * EPI_CHUNK + t.lane;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int col = n0 + (2 * k + t.grp) * EPI_CHUNK + t.lane;
-    const float b = col < p.n_out ? __ldg(bp + 2 * k * EPI_CHUNK) : 0.f;
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(t.bias + k * 128u + t.lane * 4u), "f"(b) : "memory");
+    if (col < p.n_out) r.b[k] = __ldg(bp + 2 * k * EPI_CHUNK);
   }
+}
+__device__ __forceinline__ void epi_bias_stage(const EpiParams& p, const EpiThread& t, const EpiBias& r) {
+  if (p.bias == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(t.bias + k * 128u + t.lane * 4u), "f"(r.b[k]) : "memory");
   __syncwarp();
+}
+// Load + stage in one go (kernels that cannot look one panel ahead).
+__device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiThread& t, int m0, int n0) {
+  EpiBias r;
+  epi_bias_load(p, t, m0, n0, r);
+  epi_bias_stage(p, t, r);
 }
 
 #define EPI_TIMED(slot, stmt)                                                        \
@@ -210,10 +224,9 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiThread
 // (compile-time, so the AdaGN group of every column is static).  `full`: tile completely inside the matrix.
 template <bool kStats, int C>
 __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm, const EpiThread& t, float (&v)[EPI_CHUNK],
-                                          int m0, int n0, bool rows_valid, bool row_valid, float g0, float g1, float g2,
+                                          int m0, int col0, bool rows_valid, bool row_valid, float g0, float g1, float g2,
                                           const CUtensorMap* tma_o32, const CUtensorMap* tma_o16,
                                           float (&st)[kStats ? 32 : 1], uint32_t& cnt) {
-  const int col0 = n0 + C * EPI_CHUNK;
   if (p.geom != nullptr) {
     const float4* wp = reinterpret_cast<const float4*>(p.wx + (long long)col0 * 3);
 #pragma unroll
@@ -300,8 +313,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
 }
 
 // Epilogue side (all threads of both groups).  taddr: TMEM address of (lane quadrant q, panel column 0).
-// `cnt` counts the chunks this group has processed (the loader keeps the same count per group).  epi_prefetch must
-// have been called for the same (m0, n0) by this thread.  The group's three chunks (grp, grp + 2, grp + 4) are software
+// `cnt` counts the chunks this group has processed (the loader keeps the same count per group).  The bias of (m0, n0)
+// must have been staged by this thread (epi_bias_stage / epi_prefetch).  The group's three chunks (grp, grp + 2, grp + 4) are software
 // pipelined: the TMEM load of the next chunk is issued as soon as the current one has been consumed, because
 // tcgen05.ld latency is several hundred cycles while the tensor core is streaming accumulators through TMEM.
 template <bool kStats>
@@ -352,10 +365,15 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
         v[4 * j + 3] = __uint_as_float(rr[k & 1][4 * j + 3]) + b[j].w;
       }
       if (k < 2 && n0 + (2 * k + 2 + t.grp) * EPI_CHUNK < p.n_out) tmem_ld32_issue(ta + (2 * k + 2) * EPI_CHUNK, rr[(k + 1) & 1]);
-      if (t.grp == 0)
-        epi_chunk<kStats, 2 * k>(p, sm, t, v, m0, n0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
-      else
-        epi_chunk<kStats, 2 * k + 1>(p, sm, t, v, m0, n0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
+      const int col0 = n0 + (2 * k + t.grp) * EPI_CHUNK;
+      if constexpr (kStats) {  // the AdaGN group of every column must be static: one instantiation per chunk index
+        if (t.grp == 0)
+          epi_chunk<true, 2 * k>(p, sm, t, v, m0, col0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
+        else
+          epi_chunk<true, 2 * k + 1>(p, sm, t, v, m0, col0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
+      } else {
+        epi_chunk<false, 0>(p, sm, t, v, m0, col0, rows_valid, row_valid, g0, g1, g2, tma_o32, tma_o16, st, cnt);
+      }
     }
   };
   step(std::integral_constant<int, 0>{});

@@ -220,13 +220,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t tile = 0, cnt = 0;
     long long w_accfull = 0, w_pref = 0;
     const long long t_start = clock64();
+    EpiBias bias_r;
+    if (pair < p.num_pair_blocks) epi_bias_load(p.e, et, pair * 2 * BM + (int)rank * BM, 0, bias_r);
     for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs) {
       const int m0 = pb * 2 * BM + (int)rank * BM;
       for (int nb = 0; nb < p.num_n_blocks; ++nb, ++tile) {
         const uint32_t slot = tile & 1u;
         long long tp0 = 0;
         if (GECCO_DBG_ON(p.dbg)) tp0 = clock64();
-        epi_prefetch(p.e, et, m0, nb * BN);
+        epi_bias_stage(p.e, et, bias_r);
+        // the next panel's bias is loaded under this panel
+        if (nb + 1 < p.num_n_blocks) epi_bias_load(p.e, et, m0, (nb + 1) * BN, bias_r);
+        else if (pb + num_pairs < p.num_pair_blocks) epi_bias_load(p.e, et, (pb + num_pairs) * 2 * BM + (int)rank * BM, 0, bias_r);
         if (GECCO_DBG_ON(p.dbg)) w_pref += clock64() - tp0;
         TIMED_WAIT(w_accfull, &acc_full[slot], (tile >> 1) & 1u);
         tc_fence_after_sync();

@@ -160,12 +160,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quadrant of this warp
     int it = 0;
     uint32_t cnt = 0;
+    EpiBias bias_r;
+    if ((int)blockIdx.x < num_tiles)
+      epi_bias_load(p.e, et, (blockIdx.x / p.num_n_blocks) * BM, (blockIdx.x % p.num_n_blocks) * BN, bias_r);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int slot = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (t / p.num_n_blocks) * BM;
       const int n0 = (t % p.num_n_blocks) * BN;
-      epi_prefetch(p.e, et, m0, n0);
+      epi_bias_stage(p.e, et, bias_r);
+      const int tn = t + gridDim.x;  // the next tile's bias is loaded under this tile
+      if (tn < num_tiles) epi_bias_load(p.e, et, (tn / p.num_n_blocks) * BM, (tn % p.num_n_blocks) * BN, bias_r);
       mbar_wait(&acc_full[slot], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * ACC_COLS;
