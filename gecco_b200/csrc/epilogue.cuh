@@ -167,7 +167,9 @@ struct EpiThread {
 
 __device__ __forceinline__ EpiThread epi_thread_init(const EpiSmem& sm, int grp, int tid) {
   EpiThread t;
-  t.grp = grp; t.q = tid >> 5; t.lane = tid & 31;
+  // q and the warp-level staging bases are warp-uniform: say so (shuffle), the bulk-store operands then live in uniform
+  // registers instead of being broadcast lane by lane in front of every store
+  t.grp = grp; t.q = __shfl_sync(0xffffffffu, tid >> 5, 0); t.lane = tid & 31;
   const uint32_t lane = t.lane, w = grp * 4 + t.q;
   t.x7 = (lane & 7u) << 4;
   t.xs0 = smem_u32(sm.x0) + grp * EPI_RES_BYTES + t.q * 4096u;
@@ -298,7 +300,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
   if (!(p.skip & 4)) fence_proxy_async_smem();
   __syncwarp();
   if (GECCO_DBG_ON(p.dbg)) tf2__ = clock64();
-  if (t.lane == 0 && !(p.skip & 1)) {
+  if (elect_one() && !(p.skip & 1)) {  // lane 0 (the bulk groups are per thread: the same lane waits for them)
     if (p.o32 != nullptr) tma_store_2d_addr(tma_o32, xs, col0, m0 + t.q * 32);
     if (p.o16 != nullptr) tma_store_2d_addr(tma_o16, t.s16, col0, m0 + t.q * 32);
     tma_store_commit();

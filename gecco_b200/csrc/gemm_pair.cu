@@ -86,8 +86,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_full + EPI_NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
+  const int uwarp = uniform_warp_idx();  // same value, provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const uint32_t urank = uniform_u32(rank);
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int num_kb = p.num_kb;
@@ -160,10 +162,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       long long* d = p.dbg + (long long)blockIdx.x * 32;
       d[0] = clock64() - t_start; d[1] = w_aempty; d[2] = w_bempty;
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA)
-    if (rank == 0) {
+  } else if (uwarp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA): the whole warp runs the loop
+    // (uniform control flow keeps the descriptors in uniform registers), one elected lane issues
+    if (urank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      const uint32_t sA_u = uniform_u32(smem_u32(sA)), sB_u = uniform_u32(smem_u32(sB));
+      const uint32_t tmem_u = uniform_u32(tmem_base);
       int stage = 0;
       uint32_t bphase = 0;
       uint32_t it = 0, tile = 0;
@@ -174,7 +179,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint32_t slot = tile & 1u;
           TIMED_WAIT(w_acc, &acc_empty[slot], ((tile >> 1) & 1u) ^ 1u);
           tc_fence_after_sync();
-          const uint32_t tmem_d = tmem_base + slot * ACC_COLS;
+          const uint32_t tmem_d = tmem_u + slot * ACC_COLS;
           const bool last_nb = nb == p.num_n_blocks - 1;
           for (int st = 0; st < num_st; ++st) {
             TIMED_WAIT(w_bfull, &b_full[stage], bphase);
@@ -182,22 +187,27 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               const int kb = st * kbps + kk;
               if (nb == 0) TIMED_WAIT(w_afull, &a_full[kb], it & 1u);
               tc_fence_after_sync();
-              const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * A_KB_BYTES));
-              const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * stage_bytes + kk * B_STAGE_BYTES));
+              const uint64_t da = umma_desc_k_sw128(sA_u + kb * A_KB_BYTES);
+              const uint64_t db = umma_desc_k_sw128(sB_u + stage * stage_bytes + kk * B_STAGE_BYTES);
               long long ti0 = 0;
               if (GECCO_DBG_ON(p.dbg)) ti0 = clock64();
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-              if (last_nb) umma_commit_pair(&a_empty[kb]);  // the k-block may be reloaded for the next row block
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                if (last_nb) umma_commit_pair(&a_empty[kb]);  // the k-block may be reloaded for the next row block
+              }
+              __syncwarp();
               if (GECCO_DBG_ON(p.dbg)) w_issue += clock64() - ti0;
             }
-            umma_commit_pair(&b_empty[stage]);
+            if (elect_one()) umma_commit_pair(&b_empty[stage]);
+            __syncwarp();
             if (++stage == BSTAGES) { stage = 0; bphase ^= 1u; }
           }
-          umma_commit_pair(&acc_full[slot]);
+          if (elect_one()) umma_commit_pair(&acc_full[slot]);
+          __syncwarp();
         }
       }
-      if (GECCO_DBG_ON(p.dbg)) {
+      if (GECCO_DBG_ON(p.dbg) && lane == 0) {
         long long* d = p.dbg + (long long)blockIdx.x * 32;
         d[3] = clock64() - t_start; d[4] = w_acc; d[5] = w_afull; d[6] = w_bfull; d[7] = tile; d[12] = w_issue;
       }

@@ -63,6 +63,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_full + EPI_NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
+  const int uwarp = uniform_warp_idx();  // same value, provably warp-uniform (all threads converged here)
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -115,9 +116,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (uwarp == 1) {
+    // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (uniform
+    // control flow keeps the descriptors in uniform registers, see ptx.cuh), one elected lane issues
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    const uint32_t sA_u = uniform_u32(smem_u32(sA)), sB_u = uniform_u32(smem_u32(sB));
+    const uint32_t tmem_u = uniform_u32(tmem_base);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -126,21 +130,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&acc_empty[slot], acc_phase ^ 1);
       tc_fence_after_sync();
-      const uint32_t tmem_d = tmem_base + slot * ACC_COLS;
+      const uint32_t tmem_d = tmem_u + slot * ACC_COLS;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
-        const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_STAGE_BYTES));
+        const uint64_t da = umma_desc_k_sw128(sA_u + stage * A_STAGE_BYTES);
+        const uint64_t db = umma_desc_k_sw128(sB_u + stage * B_STAGE_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // +32 B per K=16 step inside the 128 B swizzle row (address field is in 16 B units)
-          umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row (address field is in 16 B units)
+            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&acc_full[slot]);
+      if (elect_one()) umma_commit(&acc_full[slot]);
+      __syncwarp();
     }
   } else if (warp == 3 && lane == 0) {
     // ------------------------------------------------------------ residual loader

@@ -120,8 +120,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(es.res_full + EPI_NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
+  const int uwarp = uniform_warp_idx();  // same value, provably warp-uniform (all threads converged here)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const uint32_t urank = uniform_u32(rank);
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int nch = p.num_chunks;
@@ -204,12 +206,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
       if (GECCO_DBG_ON(p.dbg)) p.dbg[(long long)blockIdx.x * 32 + 3] = c_w2;
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA)
-      if (rank == 0) {
+    } else if (uwarp == 1) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA): the whole warp runs the
+      // loops (uniform control flow keeps the descriptors in uniform registers, see ptx.cuh), one elected lane issues
+      if (urank == 0) {
+        const uint32_t sA_u = uniform_u32(smem_u32(sA)), sH_u = uniform_u32(smem_u32(sH));
+        const uint32_t sW1_u = uniform_u32(smem_u32(sW1)), sW2_u = uniform_u32(smem_u32(sW2));
+        const uint32_t tmem_u = uniform_u32(tmem_base);
         constexpr uint32_t idesc1 = umma_idesc_bf16(2 * BM, HC);
         constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, 2 * W2_ROWS);
-        const uint32_t tmem_h = tmem_base + Y_COLS;
+        const uint32_t tmem_h = tmem_u + Y_COLS;
         int my_blocks = 0;
         for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs) ++my_blocks;
         const uint32_t total = (uint32_t)my_blocks * (uint32_t)nch;
@@ -224,15 +230,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             TIMED(c_w1f, mbar_wait(&w1_full[s1], ph1));
             if (j == 0) TIMED(c_af, mbar_wait(&a_full[kb], blk & 1u));
             tc_fence_after_sync();
-            const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * A_KB_BYTES));
-            const uint64_t db = umma_desc_k_sw128(smem_u32(sW1 + s1 * W1_SLOT));
+            const uint64_t da = umma_desc_k_sw128(sA_u + kb * A_KB_BYTES);
+            const uint64_t db = umma_desc_k_sw128(sW1_u + s1 * W1_SLOT);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_h, da + 2 * k, db + 2 * k, idesc1, (kb | k) ? 1u : 0u);
-            umma_commit_pair(&w1_empty[s1]);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_pair(tmem_h, da + 2 * k, db + 2 * k, idesc1, (kb | k) ? 1u : 0u);
+              umma_commit_pair(&w1_empty[s1]);
+            }
+            __syncwarp();
             if (++s1 == W1_SLOTS) { s1 = 0; ph1 ^= 1u; }
           }
-          if (j == (uint32_t)nch - 1) umma_commit_pair(a_empty);  // the A row block may be replaced
-          umma_commit_pair(h_full);
+          if (elect_one()) {
+            if (j == (uint32_t)nch - 1) umma_commit_pair(a_empty);  // the A row block may be replaced
+            umma_commit_pair(h_full);
+          }
+          __syncwarp();
         };
         first_gemm(0);
         for (uint32_t g = 0; g < total; ++g) {
@@ -247,22 +259,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (j == 0) TIMED(c_ye, mbar_wait(y_empty, (blk & 1u) ^ 1u));
           tc_fence_after_sync();
           for (int kb = 0; kb < HKB; ++kb) {
-            const uint64_t da = umma_desc_k_sw128(smem_u32(sH + kb * H_KB_BYTES));
+            const uint64_t da = umma_desc_k_sw128(sH_u + kb * H_KB_BYTES);
             for (int h = 0; h < 2; ++h) {
               TIMED(c_w2f, mbar_wait(&w2_full[s2], ph2));
               tc_fence_after_sync();
-              const uint64_t db = umma_desc_k_sw128(smem_u32(sW2 + s2 * W2_SLOT));
+              const uint64_t db = umma_desc_k_sw128(sW2_u + s2 * W2_SLOT);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16_ss_pair(tmem_base + h * (2 * W2_ROWS), da + 2 * k, db + 2 * k, idesc2, (j | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
-              umma_commit_pair(&w2_empty[s2]);
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_ss_pair(tmem_u + h * (2 * W2_ROWS), da + 2 * k, db + 2 * k, idesc2, (j | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
+                umma_commit_pair(&w2_empty[s2]);
+              }
+              __syncwarp();
               if (++s2 == W2_SLOTS) { s2 = 0; ph2 ^= 1u; }
             }
           }
-          umma_commit_pair(hc_empty);
-          if (j == (uint32_t)nch - 1) umma_commit_pair(y_full);
+          if (elect_one()) {
+            umma_commit_pair(hc_empty);
+            if (j == (uint32_t)nch - 1) umma_commit_pair(y_full);
+          }
+          __syncwarp();
         }
-        if (GECCO_DBG_ON(p.dbg)) {
+        if (GECCO_DBG_ON(p.dbg) && lane == 0) {
           long long* d = p.dbg + (long long)blockIdx.x * 32;
           d[4] = clock64() - t_start; d[5] = c_w1f; d[6] = c_af; d[7] = c_hr; d[8] = c_ye; d[9] = c_w2f; d[21] = c_hf;
         }

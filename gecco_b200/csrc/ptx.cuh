@@ -231,6 +231,23 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// ---------------------------------------------------------------- warp-uniform control flow
+// tcgen05.mma / commit / TMA take their operands from UNIFORM registers.  If the issuing code sits inside an
+// `if (lane == 0)` branch the compiler cannot prove the descriptors uniform and wraps every instruction in an
+// ELECT / R2UR.BROADCAST waterfall loop (~17 instructions, ~80 cycles per MMA).  The issuing roles therefore run their
+// loops with the whole warp (warp index made provably uniform by a shuffle) and predicate only the issue itself.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
