@@ -147,6 +147,7 @@ class UnpoolArgs(C.Structure):
         ("clouds", C.c_int32), ("rows_per_cloud", C.c_int32),
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("inducers", C.c_int32),
         ("out_bf16", C.c_void_p), ("ldo", C.c_int64),
+        ("vt_scratch", C.c_void_p),
     ]
 
 

@@ -2,10 +2,14 @@
 //   pool   (AttentionPool.forward :47-65): 64 learned queries attend over the N points of a cloud;
 //          split over key ranges (flash-decoding regime) + a small combine kernel.
 //   unpool (nn.MultiheadAttention :90,112): every point attends over the 64 inducers.
-// Round-1 implementation on warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) with cp.async
-// staging; K/V/Q come from the bf16 projections written by the tcgen05 GEMM.
+// Warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) kernels with cp.async staging; K/V/Q come from the bf16
+// projections written by the tcgen05 GEMM.  The unpool core also exists on tcgen05 / TMEM (attention_tc.cu), which
+// launch_unpool_attention prefers where its shape constraints hold.
 #include "common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
+
+#include <stdlib.h>
 
 namespace gecco {
 
@@ -418,7 +422,17 @@ static int launch_unpool_t(const gecco_unpool_args& a, cudaStream_t s) {
   return GECCO_OK;
 }
 
+// GECCO_UNPOOL_TC=0 keeps the mma.sync kernel even where the tcgen05 kernel applies (A/B measurements).
+static bool unpool_tc_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("GECCO_UNPOOL_TC");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
 int launch_unpool_attention(const gecco_unpool_args& a, cudaStream_t s) {
+  if (unpool_tc_enabled() && unpool_tc_supported(a)) return launch_unpool_tc(a, s);
   GECCO_REQUIRE(a.inducers == NI, "unpool attention: only 64 inducers are supported (got %d)", a.inducers);
   GECCO_REQUIRE(a.rows_per_cloud % 128 == 0, "unpool attention: rows_per_cloud must be a multiple of 128");
   GECCO_REQUIRE(a.ldq % 8 == 0 && a.ldkv % 8 == 0 && a.ldo % 8 == 0 && a.v_off % 8 == 0, "unpool attention: misaligned layout");

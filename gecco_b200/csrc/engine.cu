@@ -135,7 +135,7 @@ struct Workspace {
   __nv_bfloat16* y;    // [rows, C] unpool attention output
   __nv_bfloat16* big;  // [rows, max(3C, hidden, sum level_c)] k|v|q | mlp hidden | looked-up image features
   int wide;
-  __nv_bfloat16 *pooled, *hn, *hh, *h3, *khv;
+  __nv_bfloat16 *pooled, *hn, *hh, *h3, *khv, *vt;
   float *h, *h2, *partial;
   double* stats;
   long long n_stats;
@@ -178,6 +178,7 @@ Workspace carve(const gecco_engine* e, int clouds, int points, void* base) {
   w.hh = c.take<__nv_bfloat16>((size_t)w.irows * hid);
   w.h3 = c.take<__nv_bfloat16>((size_t)w.irows * C);
   w.khv = c.take<__nv_bfloat16>((size_t)w.irows * 2 * C);
+  w.vt = c.take<__nv_bfloat16>((size_t)w.irows * C);  // v transposed per cloud (tcgen05 unpool attention)
   w.h = c.take<float>((size_t)w.irows * C);
   w.h2 = c.take<float>((size_t)w.irows * C);
   w.partial = c.take<float>((size_t)clouds * d.num_heads * w.splits * I * (C / d.num_heads + 2));
@@ -406,6 +407,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       u.q = w.big + 2 * C; u.ldq = C3; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
       u.clouds = clouds; u.rows_per_cloud = Np; u.heads = H; u.head_dim = hd; u.inducers = I;
       u.out_bf16 = w.y; u.ldo = C;
+      u.vt_scratch = w.vt;
       TRYP(K_UNPOOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 4, launch_unpool_attention(u, s));
       // x = x + out_proj(attn)  (:164), bf16 copy, statistics for mlp_norm
       g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);

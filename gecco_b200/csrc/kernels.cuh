@@ -35,5 +35,8 @@ int launch_fold_gn(const float* W, const float* bias, const double* stats, doubl
                    int c_in, int c_out, int clouds, void* wb, long long ldwb, float* bb, cudaStream_t s);
 int launch_pool_attention(const gecco_pool_args& a, cudaStream_t s);
 int launch_unpool_attention(const gecco_unpool_args& a, cudaStream_t s);
+// tcgen05 / TMEM version of the unpool attention core (attention_tc.cu); needs a.vt_scratch.
+bool unpool_tc_supported(const gecco_unpool_args& a);
+int launch_unpool_tc(const gecco_unpool_args& a, cudaStream_t s);
 
 }  // namespace gecco

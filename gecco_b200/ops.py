@@ -372,7 +372,9 @@ def pool_attention(kv: Tensor, q_inducers: Tensor, *, clouds: int, rows_per_clou
 
 
 def unpool_attention(q: Tensor, khv: Tensor, *, clouds: int, rows_per_cloud: int, heads: int, head_dim: int, v_off: int,
-                     inducers: int = 64, out: Tensor | None = None) -> Tensor:
+                     inducers: int = 64, out: Tensor | None = None, tensor_cores: bool = True) -> Tensor:
+    """Attention core of the unpool MultiheadAttention; with tensor_cores the tcgen05 / TMEM kernel is used where it
+    applies (8 heads of 48 channels, rows_per_cloud % 128 == 0), see gecco_unpool_attention."""
     lib = _lib_for(q)
     assert q.dtype == torch.bfloat16 and khv.dtype == torch.bfloat16
     if out is None:
@@ -383,5 +385,8 @@ def unpool_attention(q: Tensor, khv: Tensor, *, clouds: int, rows_per_cloud: int
     a.clouds, a.rows_per_cloud = clouds, rows_per_cloud
     a.heads, a.head_dim, a.inducers = heads, head_dim, inducers
     a.out_bf16, a.ldo = out.data_ptr(), out.stride(0)
+    if tensor_cores:
+        vt = torch.empty((clouds, heads * head_dim, inducers), device=q.device, dtype=torch.bfloat16)
+        a.vt_scratch = vt.data_ptr()
     _abi.check(lib.gecco_unpool_attention(C.byref(a), _stream(q)))
     return out

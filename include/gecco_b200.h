@@ -266,6 +266,9 @@ typedef struct gecco_unpool_args {
   int32_t clouds, rows_per_cloud;
   int32_t heads, head_dim, inducers;
   void* out_bf16; int64_t ldo;
+  void* vt_scratch;   /* optional bf16 [clouds * heads * head_dim * inducers] device scratch (v transposed per cloud): when given
+                       * and heads == 8, head_dim == 48, rows_per_cloud % 128 == 0 the tcgen05 / TMEM kernel runs, otherwise
+                       * (NULL or other shapes) the mma.sync kernel */
 } gecco_unpool_args;
 int gecco_unpool_attention(const gecco_unpool_args* args, void* stream);
 

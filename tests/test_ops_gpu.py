@@ -220,17 +220,19 @@ def test_pool_attention(cuda, N, splits):
     assert err < 2e-2, err
 
 
-def test_unpool_attention(cuda):
+@pytest.mark.parametrize("tensor_cores,B,Np", [(False, 2, 256), (True, 2, 256), (True, 5, 128), (True, 70, 384)])
+def test_unpool_attention(cuda, tensor_cores, B, Np):
+    """mma.sync kernel and tcgen05 / TMEM kernel (several tiles per CTA, CTAs spanning two clouds) against torch SDPA."""
     from gecco_b200 import ops
 
-    B, H, D, I, Np = 2, 8, 48, 64, 256
+    H, D, I = 8, 48, 64
     C = H * D
     g = _gen(7)
     q = torch.randn(B * Np, C, generator=g)
     khv = torch.randn(B * I, 2 * C, generator=g)
     qd = (q * (D**-0.5 * math.log2(math.e))).to(cuda).bfloat16()
     kd = khv.to(cuda).bfloat16()
-    out = ops.unpool_attention(qd, kd, clouds=B, rows_per_cloud=Np, heads=H, head_dim=D, v_off=C)
+    out = ops.unpool_attention(qd, kd, clouds=B, rows_per_cloud=Np, heads=H, head_dim=D, v_off=C, tensor_cores=tensor_cores)
     torch.cuda.synchronize()
     qr = (qd.float().cpu() / (D**-0.5 * math.log2(math.e)) ).view(B, Np, H, D).transpose(1, 2)
     kr = kd.float().cpu().view(B, I, 2 * C)
