@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace gecco {
 
 namespace {
@@ -48,9 +50,9 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
 
 // Data-space point -> normalised image coordinates (reparam.diffusion_to_data + kornia project_points), then the
 // grid_sample grid value 2 uv - 1 (models/ray.py:71-82).
-__device__ __forceinline__ void lookup_coords(const LookupP& p, const float* __restrict__ xp, float c_in, float fx, float cx,
+__device__ __forceinline__ void lookup_coords(const LookupP& p, const float (&xyz)[3], float c_in, float fx, float cx,
                                               float fy, float cy, float& gx, float& gy) {
-  float g[3] = {c_in * __ldg(xp), c_in * __ldg(xp + 1), c_in * __ldg(xp + 2)};
+  float g[3] = {c_in * xyz[0], c_in * xyz[1], c_in * xyz[2]};
   float d[3];
   if (p.reparam == 1) {  // GaussianReparam.diffusion_to_data (reparam.py:62-64)
     for (int j = 0; j < 3; ++j) d[j] = g[j] * p.rsig[j] + p.mean[j];
@@ -79,13 +81,11 @@ __device__ __forceinline__ void lookup_coords(const LookupP& p, const float* __r
   gy = v * 2.0f - 1.0f;
 }
 
-// The four bilinear taps of one 8-channel chunk: issue the loads (zeros padding, align_corners=False).
-struct Taps {
-  uint4 q[4];
-  float w[4];
-};
-__device__ __forceinline__ void lookup_issue(const __nv_bfloat16* __restrict__ base, int H, int W, int C, float gx, float gy,
-                                             Taps& t) {
+// Bilinear tap geometry of one level (F.grid_sample, zeros padding, align_corners=False): pixel index y * W + x and
+// weight of the four taps.  A tap outside the map contributes 0: its weight is zeroed and its index is 0
+// (non-finite coordinates give NaN weights, which the validity test turns into zeros exactly like grid_sample's
+// padding).
+__device__ __forceinline__ void lookup_geom(int H, int W, float gx, float gy, int (&pix)[4], float (&w)[4], bool (&tv)[4]) {
   const float ix = ((gx + 1.0f) * W - 1.0f) / 2.0f;
   const float iy = ((gy + 1.0f) * H - 1.0f) / 2.0f;
   const float x0 = floorf(ix), y0 = floorf(iy);
@@ -93,16 +93,26 @@ __device__ __forceinline__ void lookup_issue(const __nv_bfloat16* __restrict__ b
   const bool vx0 = x0 >= 0.f && x0 <= (float)(W - 1), vx1 = x1 >= 0.f && x1 <= (float)(W - 1);
   const bool vy0 = y0 >= 0.f && y0 <= (float)(H - 1), vy1 = y1 >= 0.f && y1 <= (float)(H - 1);
   const int xi0 = vx0 ? (int)x0 : 0, xi1 = vx1 ? (int)x1 : 0, yi0 = vy0 ? (int)y0 : 0, yi1 = vy1 ? (int)y1 : 0;
-  const bool tv[4] = {vx0 && vy0, vx1 && vy0, vx0 && vy1, vx1 && vy1};
-  const int to[4] = {(yi0 * W + xi0) * C, (yi0 * W + xi1) * C, (yi1 * W + xi0) * C, (yi1 * W + xi1) * C};
-  // a tap outside the map contributes 0: its weight is zeroed (non-finite coordinates give NaN weights, which the
-  // validity test turns into zeros exactly like grid_sample's padding)
-  t.w[0] = tv[0] ? (x1 - ix) * (y1 - iy) : 0.f;
-  t.w[1] = tv[1] ? (ix - x0) * (y1 - iy) : 0.f;
-  t.w[2] = tv[2] ? (x1 - ix) * (iy - y0) : 0.f;
-  t.w[3] = tv[3] ? (ix - x0) * (iy - y0) : 0.f;
+  tv[0] = vx0 && vy0; tv[1] = vx1 && vy0; tv[2] = vx0 && vy1; tv[3] = vx1 && vy1;
+  pix[0] = yi0 * W + xi0; pix[1] = yi0 * W + xi1; pix[2] = yi1 * W + xi0; pix[3] = yi1 * W + xi1;
+  w[0] = tv[0] ? (x1 - ix) * (y1 - iy) : 0.f;
+  w[1] = tv[1] ? (ix - x0) * (y1 - iy) : 0.f;
+  w[2] = tv[2] ? (x1 - ix) * (iy - y0) : 0.f;
+  w[3] = tv[3] ? (ix - x0) * (iy - y0) : 0.f;
+}
+
+// The four bilinear taps of one 8-channel chunk: issue the loads.
+struct Taps {
+  uint4 q[4];
+  float w[4];
+};
+__device__ __forceinline__ void lookup_issue(const __nv_bfloat16* __restrict__ base, int H, int W, int C, float gx, float gy,
+                                             Taps& t) {
+  int pix[4];
+  bool tv[4];
+  lookup_geom(H, W, gx, gy, pix, t.w, tv);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) t.q[i] = tv[i] ? __ldg(reinterpret_cast<const uint4*>(base + to[i])) : make_uint4(0, 0, 0, 0);
+  for (int i = 0; i < 4; ++i) t.q[i] = tv[i] ? __ldg(reinterpret_cast<const uint4*>(base + pix[i] * C)) : make_uint4(0, 0, 0, 0);
 }
 __device__ __forceinline__ void lookup_blend(const Taps& t, float (&acc)[8]) {
 #pragma unroll
@@ -171,8 +181,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 2) lookup_kernel(const LookupP 
     const int pt2 = pt + stride;
     const bool two = pt2 < p.points;
     float gx[2], gy[2];
-    lookup_coords(p, p.xin + ((long long)cloud * p.points + pt) * 3, c_in, fx, cx, fy, cy, gx[0], gy[0]);
-    lookup_coords(p, p.xin + ((long long)cloud * p.points + (two ? pt2 : pt)) * 3, c_in, fx, cx, fy, cy, gx[1], gy[1]);
+    {
+      const float* xa = p.xin + ((long long)cloud * p.points + pt) * 3;
+      const float* xb = p.xin + ((long long)cloud * p.points + (two ? pt2 : pt)) * 3;
+      const float pa[3] = {__ldg(xa), __ldg(xa + 1), __ldg(xa + 2)}, pb[3] = {__ldg(xb), __ldg(xb + 1), __ldg(xb + 2)};
+      lookup_coords(p, pa, c_in, fx, cx, fy, cy, gx[0], gy[0]);
+      lookup_coords(p, pb, c_in, fx, cx, fy, cy, gx[1], gy[1]);
+    }
     Taps taps[2][NCH];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -226,6 +241,316 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 2) lookup_kernel(const LookupP 
     for (int i = threadIdx.x; i < p.stat_groups * 2; i += blockDim.x)
       atomicAdd(p.stats + (long long)cloud * p.stat_groups * 2 + i, static_cast<double>(sgrp[i]));
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory staged lookup (the production path when the slice of one cloud's pyramid fits in shared memory).
+//
+// The legacy kernel above gathers 4 taps x sum(C) x 2 B = 5.4 KB per point from L2 (704 MB per launch at 64 clouds x 2048
+// points), which bounds it at the L2 gather rate, far below the HBM roofline of its compulsory traffic (pyramid once +
+// output once).  Here a CTA owns (cloud, channel slice, point range): slice s of S holds channels
+// [s C_l / S, (s + 1) C_l / S) of every level, copied once into shared memory (cp.async, 16 B units, per-pixel runs stay
+// contiguous), and all of the CTA's points gather from shared memory.  Per 256-point chunk one thread per point computes
+// reparam -> projection -> tap geometry for every level into a small table (phase A); then thread (point lane, unit)
+// blends UPT 8-channel units of one level for every point of its lane (phase B): the unit -> (level, column) mapping is
+// fixed per thread, so the per-channel GroupNorm sums live in registers (packed fp32x2 arithmetic) and are reduced once
+// per CTA.  Global traffic is the compulsory traffic: each pyramid byte is read once per point range, each output row
+// segment is written once in runs of C_l / S channels.
+constexpr int LS_THREADS = 512;
+constexpr int LS_CHUNK = 256;                  // points per tap table
+constexpr int LS_SGRP_BYTES = 64 * 2 * 4;      // per-group sums (stat_groups <= 64)
+constexpr size_t LS_SMEM_MAX = 227 * 1024;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// one bf16x2 word -> two fp32 lanes (exact)
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {
+  return pack_f32x2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
+// PACKED: blend and statistics on packed fp32x2 arithmetic (FFMA2 / FADD2) instead of scalar FFMA.
+template <int UPT, bool PACKED>
+__global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const LookupP p, const int S, const int pts_per_cta) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int slice = blockIdx.x, cloud = blockIdx.y, tid = threadIdx.x;
+  const int pt_begin = blockIdx.z * pts_per_cta;
+  const int pt_end = min(p.points, pt_begin + pts_per_cta);
+
+  // geometry of this slice: 16 B units per pixel, byte offset of every level in shared memory, thread units per point
+  int nU[GECCO_MAX_LEVELS], sm_off[GECCO_MAX_LEVELS], col_off[GECCO_MAX_LEVELS];
+  int off = 0, tpp = 0, col = 0;
+#pragma unroll
+  for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
+    nU[l] = l < p.n_levels ? p.lvl_c[l] / (8 * S) : 0;
+    sm_off[l] = off;
+    col_off[l] = col;
+    off += p.lvl_h[l] * p.lvl_w[l] * nU[l] * 16;
+    tpp += nU[l] / UPT;
+    col += p.lvl_c[l];
+  }
+  float* sgrp = reinterpret_cast<float*>(lsm + off);
+  // two tap tables (chunk parity): [n_levels][LS_CHUNK] 4 x u16 pixel indices, then [n_levels][LS_CHUNK] 4 weights
+  const int tab_bytes = p.n_levels * LS_CHUNK * 24;
+  uint8_t* tab0 = lsm + off + LS_SGRP_BYTES;
+  float* csum = reinterpret_cast<float*>(tab0);  // after the point loop: per-column sums [ctot][2]
+
+  // ---- stage the slice (asynchronously; the tap table of the first chunk is computed under it)
+#pragma unroll
+  for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
+    if (nU[l] == 0) continue;
+    const int C = p.lvl_c[l], n = nU[l];
+    const int total = p.lvl_h[l] * p.lvl_w[l] * n;
+    const __nv_bfloat16* src = p.lvl_ptr[l] + (long long)cloud * p.lvl_h[l] * p.lvl_w[l] * C + slice * n * 8;
+    const uint32_t dst = smem_u32(lsm + sm_off[l]);
+    for (int i = tid; i < total; i += LS_THREADS) {
+      const int px = i / n, u = i - px * n;
+      cp_async16(dst + i * 16, src + (long long)px * C + u * 8);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // ---- fixed (point lane, unit) role of this thread: units u0 + k nU / UPT of one level, so that consecutive threads
+  // of a point read consecutive 16 B of a pixel (bank-conflict free) and write consecutive 16 B of the output row
+  const int lanes = LS_THREADS / tpp;  // points in flight
+  const int pl = tid / tpp, ut = tid - pl * tpp;
+  const bool active = pl < lanes;
+  int lv = 0, u0 = ut;
+#pragma unroll
+  for (int l = 0; l < GECCO_MAX_LEVELS - 1; ++l) {
+    if (lv == l && u0 >= nU[l] / UPT) {
+      u0 -= nU[l] / UPT;
+      lv = l + 1;
+    }
+  }
+  int my_n = 0, my_sm = 0, my_col = 0;
+#pragma unroll
+  for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
+    if (l == lv) {
+      my_n = nU[l];
+      my_sm = sm_off[l];
+      my_col = col_off[l] + slice * nU[l] * 8;
+    }
+  }
+  const uint8_t* gbase = lsm + my_sm + u0 * 16;
+  const int gstride = my_n * 16;
+  const int kstride = (my_n / UPT) * 16;  // bytes between the units of this thread
+  my_col += u0 * 8;
+  const int kcol = (my_n / UPT) * 8;
+
+  float s1[UPT][8], s2[UPT][8];
+#pragma unroll
+  for (int k = 0; k < UPT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[k][j] = s2[k][j] = 0.f;
+
+  float c_in = 1.f;
+  if (p.sigma != nullptr) {
+    const float sg = __ldg(p.sigma + (long long)cloud * p.sigma_stride);
+    c_in = 1.0f / sqrtf(p.sigma_data * p.sigma_data + sg * sg);
+  }
+  const float* Kc = p.K + (long long)cloud * 9;
+  const float fx = __ldg(Kc + 0), cx = __ldg(Kc + 2), fy = __ldg(Kc + 4), cy = __ldg(Kc + 5);
+
+  // phase A: tap geometry of every level of one point (one thread per point of the chunk) into table `par`
+  auto load_xyz = [&](int c0, float (&xyz)[3]) {
+    const float* xp = p.xin + ((long long)cloud * p.points + min(c0 + tid, pt_end - 1)) * 3;
+    xyz[0] = __ldg(xp); xyz[1] = __ldg(xp + 1); xyz[2] = __ldg(xp + 2);
+  };
+  auto write_taps = [&](int par, const float (&xyz)[3]) {
+    float gx, gy;
+    lookup_coords(p, xyz, c_in, fx, cx, fy, cy, gx, gy);
+    uint2* tidx = reinterpret_cast<uint2*>(tab0 + par * tab_bytes);
+    float4* tw = reinterpret_cast<float4*>(tab0 + par * tab_bytes + p.n_levels * LS_CHUNK * 8);
+#pragma unroll
+    for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
+      if (l >= p.n_levels) break;
+      int pix[4];
+      float w[4];
+      bool tv[4];
+      lookup_geom(p.lvl_h[l], p.lvl_w[l], gx, gy, pix, w, tv);
+      tidx[l * LS_CHUNK + tid] = make_uint2((uint32_t)pix[0] | ((uint32_t)pix[1] << 16), (uint32_t)pix[2] | ((uint32_t)pix[3] << 16));
+      tw[l * LS_CHUNK + tid] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+  };
+  if (tid < LS_CHUNK && pt_begin < pt_end) {
+    float xyz[3];
+    load_xyz(pt_begin, xyz);
+    write_taps(0, xyz);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  int par = 0;
+  for (int c0 = pt_begin; c0 < pt_end; c0 += LS_CHUNK, par ^= 1) {
+    const int cn = min(LS_CHUNK, pt_end - c0);
+    const bool prep_next = tid < LS_CHUNK && c0 + LS_CHUNK < pt_end;
+    float xyz[3];
+    if (prep_next) load_xyz(c0 + LS_CHUNK, xyz);  // in flight under phase B
+    // ---- phase B: gather + blend from shared memory
+    if (active) {
+      const uint2* my_idx = reinterpret_cast<const uint2*>(tab0 + par * tab_bytes) + lv * LS_CHUNK;
+      const float4* my_w = reinterpret_cast<const float4*>(tab0 + par * tab_bytes + p.n_levels * LS_CHUNK * 8) + lv * LS_CHUNK;
+      // the table entry of the next point is fetched one iteration ahead (shortens the dependent LDS -> LDS chain)
+      uint2 ix_n = make_uint2(0u, 0u);
+      float4 w4_n = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pl < cn) {
+        ix_n = my_idx[pl];
+        w4_n = my_w[pl];
+      }
+      for (int i = pl; i < cn; i += lanes) {
+        const uint2 ix = ix_n;
+        const float4 w4 = w4_n;
+        if (i + lanes < cn) {
+          ix_n = my_idx[i + lanes];
+          w4_n = my_w[i + lanes];
+        }
+        const uint32_t px[4] = {ix.x & 0xffffu, ix.x >> 16, ix.y & 0xffffu, ix.y >> 16};
+        const float wt[4] = {w4.x, w4.y, w4.z, w4.w};
+        uint4 q[4][UPT];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int k = 0; k < UPT; ++k) q[t][k] = *reinterpret_cast<const uint4*>(gbase + px[t] * gstride + k * kstride);
+        __nv_bfloat16* orow = p.out16 + ((long long)cloud * p.rows_per_cloud + c0 + i) * p.ldo16 + my_col;
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+          uint32_t o[4];
+          if (PACKED) {
+            uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint64_t ww = pack_f32x2(wt[t], wt[t]);
+              acc[0] = fma_f32x2(bf16x2_to_f32x2(q[t][k].x), ww, acc[0]);
+              acc[1] = fma_f32x2(bf16x2_to_f32x2(q[t][k].y), ww, acc[1]);
+              acc[2] = fma_f32x2(bf16x2_to_f32x2(q[t][k].z), ww, acc[2]);
+              acc[3] = fma_f32x2(bf16x2_to_f32x2(q[t][k].w), ww, acc[3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint64_t a1 = pack_f32x2(s1[k][2 * j], s1[k][2 * j + 1]), a2 = pack_f32x2(s2[k][2 * j], s2[k][2 * j + 1]);
+              a1 = add_f32x2(a1, acc[j]);
+              a2 = fma_f32x2(acc[j], acc[j], a2);
+              unpack_f32x2(a1, s1[k][2 * j], s1[k][2 * j + 1]);
+              unpack_f32x2(a2, s2[k][2 * j], s2[k][2 * j + 1]);
+              float lo, hi;
+              unpack_f32x2(acc[j], lo, hi);
+              o[j] = pack_bf16x2(lo, hi);
+            }
+          } else {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float f[8];
+              bf16x8_to_float(q[t][k], f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wt[t], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s1[k][j] += acc[j];
+              s2[k][j] = fmaf(acc[j], acc[j], s2[k][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(acc[2 * j], acc[2 * j + 1]);
+          }
+          *reinterpret_cast<uint4*>(orow + k * kcol) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    if (prep_next) write_taps(par ^ 1, xyz);
+    __syncthreads();
+  }
+
+  // ---- GroupNorm statistics (models/ray.py:53): per-column sums -> per-group sums -> global accumulators
+  if (p.stats != nullptr) {
+    for (int i = tid; i < p.ctot * 2; i += LS_THREADS) csum[i] = 0.f;
+    for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS) sgrp[i] = 0.f;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < UPT; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float* c = csum + (my_col + k * kcol + j) * 2;
+          atomicAdd(c + 0, s1[k][j]);
+          atomicAdd(c + 1, s2[k][j]);
+        }
+    }
+    __syncthreads();
+    const int gsz = p.ctot / p.stat_groups;
+    for (int i = tid; i < p.ctot; i += LS_THREADS) {
+      const float a = csum[i * 2], b = csum[i * 2 + 1];
+      if (a != 0.f || b != 0.f) {  // columns of other slices stay zero
+        atomicAdd(&sgrp[(i / gsz) * 2], a);
+        atomicAdd(&sgrp[(i / gsz) * 2 + 1], b);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS)
+      if (sgrp[i] != 0.f) atomicAdd(p.stats + (long long)cloud * p.stat_groups * 2 + i, static_cast<double>(sgrp[i]));
+  }
+}
+
+// Slice count of the staged kernel: the smallest S that divides every level into whole 8-channel units, fits one
+// slice of one cloud (plus the tap table) in shared memory and gives every unit a thread.  0 = not applicable.
+// GECCO_LOOKUP_SLICES overrides (0 forces the legacy global-gather kernel).
+struct StagedPlan {
+  int S, upt;
+  size_t smem;
+};
+StagedPlan plan_staged(const LookupP& p, int stat_groups) {
+  StagedPlan none = {0, 0, 0};
+  if (p.out16 == nullptr || p.out32 != nullptr) return none;
+  if (stat_groups > 64) return none;
+  int forced = -1;
+  if (const char* v = getenv("GECCO_LOOKUP_SLICES")) forced = atoi(v);
+  if (forced == 0) return none;
+  for (int l = 0; l < p.n_levels; ++l)
+    if (p.lvl_h[l] * p.lvl_w[l] > 65535) return none;
+  static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48};
+  for (int S : cand) {
+    if (forced > 0 && S != forced) continue;
+    bool ok = true, even = true;
+    size_t bytes = 0;
+    int units = 0;
+    for (int l = 0; l < p.n_levels; ++l) {
+      if (p.lvl_c[l] % (8 * S) != 0) { ok = false; break; }
+      const int n = p.lvl_c[l] / (8 * S);
+      even = even && (n % 2 == 0);
+      units += n;
+      bytes += (size_t)p.lvl_h[l] * p.lvl_w[l] * n * 16;
+    }
+    if (!ok) continue;
+    const int upt = even ? 2 : 1;
+    if (units / upt > LS_THREADS) continue;
+    size_t tab = (size_t)2 * p.n_levels * LS_CHUNK * 24;  // two tap tables
+    if ((size_t)p.ctot * 8 > tab) tab = (size_t)p.ctot * 8;
+    const size_t total = bytes + LS_SGRP_BYTES + tab;
+    if (total > LS_SMEM_MAX) continue;
+    return {S, upt, total};
+  }
+  return none;
 }
 
 // GroupNorm (no affine) followed by Linear, folded per cloud (models/ray.py:52-55):
@@ -320,6 +645,31 @@ int launch_lookup(const gecco_lookup_args& a, cudaStream_t s) {
   p.stats = a.stats; p.stat_groups = a.stats ? a.stat_groups : 0;
   if (a.points == 0 || a.clouds == 0) return GECCO_OK;
   GECCO_REQUIRE(!a.stats || ctot / a.stat_groups >= 8, "lookup: GroupNorm groups must be at least 8 channels wide");
+  const StagedPlan plan = plan_staged(p, p.stat_groups);
+  if (plan.S > 0) {
+    // (slice, cloud, point range): point ranges only when clouds x slices leave SMs idle
+    int z = sm_count() / (a.clouds * plan.S);
+    if (z < 1) z = 1;
+    int per = ceil_div(ceil_div(a.points, z), 32) * 32;
+    z = ceil_div(a.points, per);
+    dim3 grid(plan.S, a.clouds, z);
+    const char* sc = getenv("GECCO_LOOKUP_SCALAR");  // A/B switch: scalar FFMA instead of packed fp32x2 arithmetic
+    const bool packed = !(sc != nullptr && sc[0] == '1');
+    auto go = [&](auto kern, bool& done) {
+      if (!done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM_MAX);
+        done = true;
+      }
+      kern<<<grid, LS_THREADS, plan.smem, s>>>(p, plan.S, per);
+    };
+    static bool attr_done[4] = {false, false, false, false};
+    if (plan.upt == 2 && packed) go(lookup_staged_kernel<2, true>, attr_done[0]);
+    else if (plan.upt == 2) go(lookup_staged_kernel<2, false>, attr_done[1]);
+    else if (packed) go(lookup_staged_kernel<1, true>, attr_done[2]);
+    else go(lookup_staged_kernel<1, false>, attr_done[3]);
+    GECCO_CHECK_LAUNCH("lookup_staged_kernel");
+    return GECCO_OK;
+  }
   dim3 grid(ceil_div(a.points, LK_WARPS * LK_POINTS_PER_WARP), a.clouds);
   const size_t sm = p.stat_groups * 2 * sizeof(float);
   switch (ceil_div(ctot, 256)) {

@@ -178,6 +178,43 @@ def test_lookup(cuda, kind):
     assert (folded - refp).abs().max().item() < 5e-2
 
 
+@pytest.mark.parametrize("sizes,N,slices", [((34, 17, 8), 333, None), ((34, 17, 8), 2048, "2"), ((34, 17, 8), 700, "4"),
+                                            ((34, 17, 8), 257, "12"), ((64, 32, 16), 1000, None), ((9, 5, 3), 64, "1")])
+def test_lookup_staged_matches_global_gather(cuda, monkeypatch, sizes, N, slices):
+    """The shared-memory staged lookup (production path, bf16 output only) against the global-gather kernel: same
+    taps, same fp32 blend order -> bit-identical rows; statistics agree to fp32 summation order."""
+    from gecco_b200 import ops
+
+    B, Np = 3, (N + 127) // 128 * 128
+    g = _gen(11)
+    dims = (96, 192, 384)
+    levels = [ops.pack_features(torch.randn(B, c, s, s, generator=g).to(cuda)) for c, s in zip(dims, sizes)]
+    K = torch.tensor([[1.0859, 0, 0.4964], [0, 1.0859, 0.4964], [0, 0, 1]]).expand(B, 3, 3).contiguous().to(cuda)
+    xin = (torch.randn(B, N, 3, generator=g) * 2).to(cuda)
+    xin[0, :5] = float("nan")  # non-finite coordinates gather zeros (grid_sample padding)
+    sigma = torch.tensor([0.5, 4.0, 80.0]).to(cuda)
+    kw = dict(reparam_kind=1, mean=[0.0, 0.0, 1.0], sigma_r=[0.15] * 3, sigma=sigma, rows_per_cloud=Np)
+
+    def run():
+        stats = torch.zeros(B, 16, 2, dtype=torch.float64, device=cuda)
+        out = torch.full((B * Np, 672), 7.0, device=cuda, dtype=torch.bfloat16)
+        ops.lookup(xin, levels, K, out_bf16=out, stats=stats, **kw)
+        torch.cuda.synchronize()
+        return out.view(B, Np, 672), stats
+
+    monkeypatch.setenv("GECCO_LOOKUP_SLICES", "0")
+    ref, ref_stats = run()
+    if slices is None:
+        monkeypatch.delenv("GECCO_LOOKUP_SLICES")
+    else:
+        monkeypatch.setenv("GECCO_LOOKUP_SLICES", slices)
+    got, stats = run()
+    assert torch.equal(got[:, :N].view(torch.int16), ref[:, :N].view(torch.int16))
+    assert torch.equal(got[:, N:], ref[:, N:])  # padding rows untouched by both
+    assert got[0, :5].abs().max().item() == 0.0
+    assert torch.allclose(stats, ref_stats, rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("kind,dtype", [("gaussian", torch.float32), ("uvl", torch.float32), ("uvl", torch.float64)])
 def test_reparam_roundtrip(cuda, kind, dtype):
     from gecco_b200 import ops
