@@ -4,7 +4,7 @@
 //   unpool (nn.MultiheadAttention :90,112): every point attends over the 64 inducers.
 // Warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) kernels with cp.async staging; K/V/Q come from the bf16
 // projections written by the tcgen05 GEMM.  The unpool core also exists on tcgen05 / TMEM (attention_tc.cu), which
-// launch_unpool_attention prefers where its shape constraints hold.
+// launch_unpool_attention prefers where its shape constraints hold; likewise the pool core (attention_pool_tc.cu).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -372,7 +372,24 @@ unpool_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __n
 
 }  // namespace
 
+// GECCO_POOL_TC=0 keeps the mma.sync kernel even where the tcgen05 kernel applies (A/B measurements).
+static bool pool_tc_enabled() {
+  const char* v = getenv("GECCO_POOL_TC");
+  return !(v != nullptr && v[0] == '0');
+}
+
 int launch_pool_attention(const gecco_pool_args& a, cudaStream_t s) {
+  if (pool_tc_enabled() && pool_tc_supported(a)) {
+    int nsplit = 1;
+    if (int rc = launch_pool_tc(a, s, &nsplit)) return rc;
+    if (nsplit > 1) {
+      const int rows = a.clouds * a.heads * NI;
+      pool_combine_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(a.partial, a.heads, nsplit, a.head_dim,
+                                                           static_cast<__nv_bfloat16*>(a.out_bf16), a.ldo, rows);
+      GECCO_CHECK_LAUNCH("pool_combine_kernel");
+    }
+    return GECCO_OK;
+  }
   GECCO_REQUIRE(a.inducers == NI, "pool attention: only 64 inducers are supported (got %d)", a.inducers);
   GECCO_REQUIRE(a.head_dim == 32 || a.head_dim == 48 || a.head_dim == 64, "pool attention: head_dim must be 32, 48 or 64 (got %d)", a.head_dim);
   GECCO_REQUIRE(a.rows_per_cloud % KT == 0, "pool attention: rows_per_cloud must be a multiple of 64");

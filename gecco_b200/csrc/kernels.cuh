@@ -39,4 +39,9 @@ int launch_unpool_attention(const gecco_unpool_args& a, cudaStream_t s);
 bool unpool_tc_supported(const gecco_unpool_args& a);
 int launch_unpool_tc(const gecco_unpool_args& a, cudaStream_t s);
 
+// tcgen05 / TMEM version of the pool attention core (attention_pool_tc.cu).  *splits_used > 1: the result was left as
+// key-split partials in a.partial (pool_combine_kernel finishes); 1: a.out_bf16 is final.
+bool pool_tc_supported(const gecco_pool_args& a);
+int launch_pool_tc(const gecco_pool_args& a, cudaStream_t s, int* splits_used);
+
 }  // namespace gecco

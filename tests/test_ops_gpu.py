@@ -233,15 +233,20 @@ def test_reparam_roundtrip(cuda, kind, dtype):
         assert (data.cpu() - (diff * torch.tensor(sig, dtype=dtype) + torch.tensor(mean, dtype=dtype))).abs().max() < 1e-6
 
 
-@pytest.mark.parametrize("N,splits", [(2048, 1), (2048, 4), (300, 2)])
-def test_pool_attention(cuda, N, splits):
+@pytest.mark.parametrize("tensor_cores,B,N,splits", [(False, 2, 2048, 1), (False, 2, 2048, 4), (False, 2, 300, 2),
+                                                     (True, 2, 2048, 1), (True, 2, 2048, 4), (True, 2, 300, 2),
+                                                     (True, 3, 1000, 3), (True, 80, 640, 1), (True, 1, 128, 1)])
+def test_pool_attention(cuda, monkeypatch, tensor_cores, B, N, splits):
+    """mma.sync kernel and tcgen05 / TMEM kernel (key splits + combine, ragged last tile, several items per warpgroup)
+    against torch SDPA.  Padding rows hold finite non-zero keys / values that must be masked out."""
     from gecco_b200 import ops
 
-    B, H, D, I = 2, 8, 48, 64
+    monkeypatch.setenv("GECCO_POOL_TC", "1" if tensor_cores else "0")
+    H, D, I = 8, 48, 64
     C = H * D
     Np = (N + 127) // 128 * 128
     g = _gen(6)
-    kv = torch.zeros(B, Np, 3 * C)
+    kv = torch.full((B, Np, 3 * C), 3.0)
     kv[:, :N] = torch.randn(B, N, 3 * C, generator=g)
     ind = torch.randn(1, H, I, D, generator=g)
     kvd = kv.to(cuda).bfloat16().reshape(B * Np, 3 * C)
