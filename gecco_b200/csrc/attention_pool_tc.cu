@@ -313,59 +313,83 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
       const int nvalid = p.valid_rows - c.tile * TM;  // points of this tile that exist (>= 1)
       mbar_wait(&s_full[w], n & 1u);
       tc_fence_after_sync();
-      // pass 1: row maximum
-      float mx = m;
+      // Reference exponent of this unit.  The first unit of an item takes the row maximum in a pass of its own; later
+      // units keep the reference reached so far (any reference gives the same softmax; TMEM is read once instead of
+      // twice) and move it afterwards if the unit raised the maximum.
+      float mref = m;
+      if (c.first_of_item(p)) {
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int cb = 0; cb < TM; cb += 32) {
-        uint32_t s[32];
-        tmem_ld32(t_addr + cb, s);
-        tmem_ld_wait();
-        if (nvalid >= cb + 32) {
+        for (int cb = 0; cb < TM; cb += 32) {
+          uint32_t s[32];
+          tmem_ld32(t_addr + cb, s);
+          tmem_ld_wait();
+          if (nvalid >= cb + 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-        } else {
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cb + i < nvalid ? __uint_as_float(s[i]) : -INFINITY);
-        }
-      }
-      const float alpha = ex2f(m - mx);  // first tile: 2^-inf = 0
-      m = mx;
-      // pass 2: P = 2^(S - m), bf16, into the swizzled K-major k-blocks
-      float sum = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < TM; cb += 32) {
-        uint32_t s[32];
-        tmem_ld32(t_addr + cb, s);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (nvalid >= cb + 32) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = ex2f(__uint_as_float(s[2 * i]) - mx), b = ex2f(__uint_as_float(s[2 * i + 1]) - mx);
-            sum += a + b;
-            pk[i] = pack_bf16x2(a, b);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = cb + 2 * i < nvalid ? ex2f(__uint_as_float(s[2 * i]) - mx) : 0.f;
-            const float b = cb + 2 * i + 1 < nvalid ? ex2f(__uint_as_float(s[2 * i + 1]) - mx) : 0.f;
-            sum += a + b;
-            pk[i] = pack_bf16x2(a, b);
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, cb + i < nvalid ? __uint_as_float(s[i]) : -INFINITY);
           }
         }
-        const uint32_t kb_row = p_row + (cb >> 6) * (TM * 128);  // k-block of 64 points
-        const uint32_t ch0 = (cb & 32) >> 3;                     // first 16 B chunk of these 32 points
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          sts128(kb_row + (((ch0 + i) << 4) ^ x7), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        mref = mx;
+        m = mx;
       }
-      l = l * alpha + sum;
+      // P = 2^(S - mref), bf16, into the swizzled K-major k-blocks; the unit's own maximum on the side
+      float sum, umax;
+      for (;;) {
+        sum = 0.f;
+        umax = -INFINITY;
+#pragma unroll 1
+        for (int cb = 0; cb < TM; cb += 32) {
+          uint32_t s[32];
+          tmem_ld32(t_addr + cb, s);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (nvalid >= cb + 32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float s0 = __uint_as_float(s[2 * i]), s1 = __uint_as_float(s[2 * i + 1]);
+              umax = fmaxf(umax, fmaxf(s0, s1));
+              const float a = ex2f(s0 - mref), b = ex2f(s1 - mref);
+              sum += a + b;
+              pk[i] = pack_bf16x2(a, b);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool v0 = cb + 2 * i < nvalid, v1 = cb + 2 * i + 1 < nvalid;
+              const float s0 = v0 ? __uint_as_float(s[2 * i]) : -INFINITY, s1 = v1 ? __uint_as_float(s[2 * i + 1]) : -INFINITY;
+              umax = fmaxf(umax, fmaxf(s0, s1));
+              const float a = ex2f(s0 - mref), b = ex2f(s1 - mref);  // 2^-inf = 0
+              sum += a + b;
+              pk[i] = pack_bf16x2(a, b);
+            }
+          }
+          const uint32_t kb_row = p_row + (cb >> 6) * (TM * 128);  // k-block of 64 points
+          const uint32_t ch0 = (cb & 32) >> 3;                     // first 16 B chunk of these 32 points
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(kb_row + (((ch0 + i) << 4) ^ x7), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        // a jump of the maximum by more than 2^64 would overflow the exponentials: redo the unit (warp-uniform, the
+        // TMEM loads are collective) with the reference moved first
+        if (!__any_sync(0xffffffffu, umax > mref + 64.f)) break;
+        if (umax > mref) {
+          const float r = ex2f(mref - umax);
+          l *= r;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) acc[d] *= r;
+          mref = umax;
+          m = umax;
+        }
+      }
+      l += sum;
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[w]);
-      // O of this unit
+      // O of this unit (same reference as acc)
       mbar_wait(&o_full[w], n & 1u);
       tc_fence_after_sync();
       {
@@ -378,7 +402,14 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_read[w]);
 #pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] = fmaf(acc[d], alpha, __uint_as_float(o[d]));
+        for (int d = 0; d < HD; ++d) acc[d] += __uint_as_float(o[d]);
+      }
+      if (umax > m) {  // move the reference for the following units
+        const float r = ex2f(m - umax);
+        l *= r;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] *= r;
+        m = umax;
       }
       ++n;
       if (c.last_of_item()) {

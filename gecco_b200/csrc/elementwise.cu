@@ -15,9 +15,12 @@ constexpr int STAT_ROWS = 64;
 
 __global__ void group_stats_kernel(const float* __restrict__ x, long long ldx, int rows_per_cloud, int valid_rows,
                                    int C, int gs, double* __restrict__ stats) {
-  extern __shared__ float sgrp[];  // [C/gs][2]
+  // [C/gs][2] per-block partial sums.  Double: the shared-memory atomics arrive in any order, and fp32 partials would
+  // make the statistics (and everything folded from them) differ in the last bit from run to run.
+  extern __shared__ double sgrp_d[];
+  double* sgrp = sgrp_d;
   const int ngroups = C / gs;
-  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.f;
+  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.0;
   __syncthreads();
   const int cloud = blockIdx.y;
   const int r0 = blockIdx.x * STAT_ROWS;
@@ -35,13 +38,13 @@ __global__ void group_stats_kernel(const float* __restrict__ x, long long ldx, i
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int g = (cq * 4 + j) / gs;
-      atomicAdd(&sgrp[g * 2], s1[j]);
-      atomicAdd(&sgrp[g * 2 + 1], s2[j]);
+      atomicAdd(&sgrp[g * 2], static_cast<double>(s1[j]));
+      atomicAdd(&sgrp[g * 2 + 1], static_cast<double>(s2[j]));
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x)
-    atomicAdd(stats + (long long)cloud * ngroups * 2 + i, static_cast<double>(sgrp[i]));
+    atomicAdd(stats + (long long)cloud * ngroups * 2 + i, sgrp[i]);
 }
 
 // mean / rstd of normalisation group `g` (of `gs` channels) from statistics kept at `sgs`-channel
@@ -229,9 +232,10 @@ __global__ void lift_kernel(const float* __restrict__ xin, const float* __restri
                             float sigma_data, const float* __restrict__ w, const float* __restrict__ b,
                             int rows_per_cloud, int valid_rows, int C, int gs, float* __restrict__ x, long long ldx,
                             __nv_bfloat16* __restrict__ xb, long long ldxb, double* __restrict__ stats) {
-  extern __shared__ float sgrp[];
+  extern __shared__ double sgrp_d[];  // double partials: order-independent in practice (see group_stats_kernel)
+  double* sgrp = sgrp_d;
   const int ngroups = C / gs;
-  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.f;
+  for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x) sgrp[i] = 0.0;
   __syncthreads();
   const int cloud = blockIdx.y;
   const int r0 = blockIdx.x * LIFT_ROWS;
@@ -273,15 +277,15 @@ __global__ void lift_kernel(const float* __restrict__ xin, const float* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = (cq * 4 + j) / gs;
-        atomicAdd(&sgrp[g * 2], s1[j]);
-        atomicAdd(&sgrp[g * 2 + 1], s2[j]);
+        atomicAdd(&sgrp[g * 2], static_cast<double>(s1[j]));
+        atomicAdd(&sgrp[g * 2 + 1], static_cast<double>(s2[j]));
       }
     }
   }
   if (stats != nullptr) {
     __syncthreads();
     for (int i = threadIdx.x; i < ngroups * 2; i += blockDim.x)
-      atomicAdd(stats + (long long)cloud * ngroups * 2 + i, static_cast<double>(sgrp[i]));
+      atomicAdd(stats + (long long)cloud * ngroups * 2 + i, sgrp[i]);
   }
 }
 
@@ -511,7 +515,7 @@ int launch_group_stats(const float* x, long long ldx, int clouds, int rows_per_c
   GECCO_REQUIRE(ldx % 4 == 0, "group_stats: ldx must be a multiple of 4");
   dim3 grid(ceil_div(valid_rows, STAT_ROWS), clouds);
   const int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
-  group_stats_kernel<<<grid, threads, (C / gs) * 2 * sizeof(float), s>>>(x, ldx, rows_per_cloud, valid_rows, C, gs, stats);
+  group_stats_kernel<<<grid, threads, (C / gs) * 2 * sizeof(double), s>>>(x, ldx, rows_per_cloud, valid_rows, C, gs, stats);
   GECCO_CHECK_LAUNCH("group_stats_kernel");
   return GECCO_OK;
 }
@@ -557,7 +561,7 @@ int launch_lift(const gecco_lift_args& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.rows_per_cloud, LIFT_ROWS), a.clouds);
   const int threads = a.c / 4 < 256 ? ((a.c / 4 + 31) / 32) * 32 : 256;
   const int gs = a.stats ? a.stat_gs : a.c;
-  lift_kernel<<<grid, threads, (a.c / gs) * 2 * sizeof(float), s>>>(a.xin, a.sigma, a.sigma_stride, a.sigma_data, a.w, a.b,
+  lift_kernel<<<grid, threads, (a.c / gs) * 2 * sizeof(double), s>>>(a.xin, a.sigma, a.sigma_stride, a.sigma_data, a.w, a.b,
                                                                    a.rows_per_cloud, a.valid_rows, a.c, gs, a.x, a.ldx,
                                                                    static_cast<__nv_bfloat16*>(a.x_bf16), a.ldxb, a.stats);
   GECCO_CHECK_LAUNCH("lift_kernel");

@@ -130,11 +130,11 @@ __device__ __forceinline__ void lookup_blend(const Taps& t, float (&acc)[8]) {
 // independent 16 B gathers per lane) because the kernel is bound by the latency of the L2-resident gathers.
 template <int NCH>
 __global__ void __launch_bounds__(LK_WARPS * 32, 2) lookup_kernel(const LookupP p) {
-  extern __shared__ float sgrp[];  // [stat_groups][2]
+  extern __shared__ double sgrp[];  // [stat_groups][2]; double: order-independent partial sums
   const int cloud = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.stats != nullptr) {
-    for (int i = threadIdx.x; i < p.stat_groups * 2; i += blockDim.x) sgrp[i] = 0.f;
+    for (int i = threadIdx.x; i < p.stat_groups * 2; i += blockDim.x) sgrp[i] = 0.0;
     __syncthreads();
   }
   // fixed chunk -> (level, channel) assignment of this lane
@@ -230,16 +230,16 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 2) lookup_kernel(const LookupP 
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       if (ch_ptr[k] == nullptr) continue;
-      atomicAdd(&sgrp[gA[k] * 2], sA1[k]);
-      atomicAdd(&sgrp[gA[k] * 2 + 1], sA2[k]);
+      atomicAdd(&sgrp[gA[k] * 2], static_cast<double>(sA1[k]));
+      atomicAdd(&sgrp[gA[k] * 2 + 1], static_cast<double>(sA2[k]));
       if (bnd[k] < 8) {
-        atomicAdd(&sgrp[(gA[k] + 1) * 2], sB1[k]);
-        atomicAdd(&sgrp[(gA[k] + 1) * 2 + 1], sB2[k]);
+        atomicAdd(&sgrp[(gA[k] + 1) * 2], static_cast<double>(sB1[k]));
+        atomicAdd(&sgrp[(gA[k] + 1) * 2 + 1], static_cast<double>(sB2[k]));
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.stat_groups * 2; i += blockDim.x)
-      atomicAdd(p.stats + (long long)cloud * p.stat_groups * 2 + i, static_cast<double>(sgrp[i]));
+      atomicAdd(p.stats + (long long)cloud * p.stat_groups * 2 + i, sgrp[i]);
   }
 }
 
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 2) lookup_kernel(const LookupP 
 // segment is written once in runs of C_l / S channels.
 constexpr int LS_THREADS = 512;
 constexpr int LS_CHUNK = 256;                  // points per tap table
-constexpr int LS_SGRP_BYTES = 64 * 2 * 4;      // per-group sums (stat_groups <= 64)
+constexpr int LS_SGRP_BYTES = 64 * 2 * 8;      // per-group sums (stat_groups <= 64), double
 constexpr size_t LS_SMEM_MAX = 227 * 1024;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -307,11 +307,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
     tpp += nU[l] / UPT;
     col += p.lvl_c[l];
   }
-  float* sgrp = reinterpret_cast<float*>(lsm + off);
+  double* sgrp = reinterpret_cast<double*>(lsm + off);
   // two tap tables (chunk parity): [n_levels][LS_CHUNK] 4 x u16 pixel indices, then [n_levels][LS_CHUNK] 4 weights
   const int tab_bytes = p.n_levels * LS_CHUNK * 24;
   uint8_t* tab0 = lsm + off + LS_SGRP_BYTES;
-  float* csum = reinterpret_cast<float*>(tab0);  // after the point loop: per-column sums [ctot][2]
+  double* csum = reinterpret_cast<double*>(tab0);  // after the point loop: per-column sums [ctot][2] (double: the
+                                                   // shared-memory atomics arrive in any order)
 
   // ---- stage the slice (asynchronously; the tap table of the first chunk is computed under it)
 #pragma unroll
@@ -484,31 +485,31 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
 
   // ---- GroupNorm statistics (models/ray.py:53): per-column sums -> per-group sums -> global accumulators
   if (p.stats != nullptr) {
-    for (int i = tid; i < p.ctot * 2; i += LS_THREADS) csum[i] = 0.f;
-    for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS) sgrp[i] = 0.f;
+    for (int i = tid; i < p.ctot * 2; i += LS_THREADS) csum[i] = 0.0;
+    for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS) sgrp[i] = 0.0;
     __syncthreads();
     if (active) {
 #pragma unroll
       for (int k = 0; k < UPT; ++k)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float* c = csum + (my_col + k * kcol + j) * 2;
-          atomicAdd(c + 0, s1[k][j]);
-          atomicAdd(c + 1, s2[k][j]);
+          double* c = csum + (my_col + k * kcol + j) * 2;
+          atomicAdd(c + 0, static_cast<double>(s1[k][j]));
+          atomicAdd(c + 1, static_cast<double>(s2[k][j]));
         }
     }
     __syncthreads();
     const int gsz = p.ctot / p.stat_groups;
     for (int i = tid; i < p.ctot; i += LS_THREADS) {
-      const float a = csum[i * 2], b = csum[i * 2 + 1];
-      if (a != 0.f || b != 0.f) {  // columns of other slices stay zero
+      const double a = csum[i * 2], b = csum[i * 2 + 1];
+      if (a != 0.0 || b != 0.0) {  // columns of other slices stay zero
         atomicAdd(&sgrp[(i / gsz) * 2], a);
         atomicAdd(&sgrp[(i / gsz) * 2 + 1], b);
       }
     }
     __syncthreads();
     for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS)
-      if (sgrp[i] != 0.f) atomicAdd(p.stats + (long long)cloud * p.stat_groups * 2 + i, static_cast<double>(sgrp[i]));
+      if (sgrp[i] != 0.0) atomicAdd(p.stats + (long long)cloud * p.stat_groups * 2 + i, sgrp[i]);
   }
 }
 
@@ -528,9 +529,13 @@ StagedPlan plan_staged(const LookupP& p, int stat_groups) {
   if (forced == 0) return none;
   for (int l = 0; l < p.n_levels; ++l)
     if (p.lvl_h[l] * p.lvl_w[l] > 65535) return none;
+  // Measured at 64 clouds x 2048 points (tools/lookup_time.py): 137^2 pyramids (S = 2) 105 us against 228 us for the
+  // global-gather kernel; 256^2 pyramids need S = 12 (7 threads per point, a tap-table entry per 8 channels) and are
+  // slower than the global gather (270 against 236 us), so the automatic choice stops at S = 4.
   static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48};
   for (int S : cand) {
     if (forced > 0 && S != forced) continue;
+    if (forced < 0 && S > 4) break;
     bool ok = true, even = true;
     size_t bytes = 0;
     int units = 0;
@@ -545,7 +550,7 @@ StagedPlan plan_staged(const LookupP& p, int stat_groups) {
     const int upt = even ? 2 : 1;
     if (units / upt > LS_THREADS) continue;
     size_t tab = (size_t)2 * p.n_levels * LS_CHUNK * 24;  // two tap tables
-    if ((size_t)p.ctot * 8 > tab) tab = (size_t)p.ctot * 8;
+    if ((size_t)p.ctot * 16 > tab) tab = (size_t)p.ctot * 16;  // per-column sums alias the tables
     const size_t total = bytes + LS_SGRP_BYTES + tab;
     if (total > LS_SMEM_MAX) continue;
     return {S, upt, total};
@@ -671,7 +676,7 @@ int launch_lookup(const gecco_lookup_args& a, cudaStream_t s) {
     return GECCO_OK;
   }
   dim3 grid(ceil_div(a.points, LK_WARPS * LK_POINTS_PER_WARP), a.clouds);
-  const size_t sm = p.stat_groups * 2 * sizeof(float);
+  const size_t sm = p.stat_groups * 2 * sizeof(double);
   switch (ceil_div(ctot, 256)) {
     case 1: lookup_kernel<1><<<grid, LK_WARPS * 32, sm, s>>>(p); break;
     case 2: lookup_kernel<2><<<grid, LK_WARPS * 32, sm, s>>>(p); break;

@@ -179,7 +179,7 @@ def test_lookup(cuda, kind):
 
 
 @pytest.mark.parametrize("sizes,N,slices", [((34, 17, 8), 333, None), ((34, 17, 8), 2048, "2"), ((34, 17, 8), 700, "4"),
-                                            ((34, 17, 8), 257, "12"), ((64, 32, 16), 1000, None), ((9, 5, 3), 64, "1")])
+                                            ((34, 17, 8), 257, "12"), ((64, 32, 16), 1000, "12"), ((9, 5, 3), 64, "1")])
 def test_lookup_staged_matches_global_gather(cuda, monkeypatch, sizes, N, slices):
     """The shared-memory staged lookup (production path, bf16 output only) against the global-gather kernel: same
     taps, same fp32 blend order -> bit-identical rows; statistics agree to fp32 summation order."""
@@ -235,7 +235,8 @@ def test_reparam_roundtrip(cuda, kind, dtype):
 
 @pytest.mark.parametrize("tensor_cores,B,N,splits", [(False, 2, 2048, 1), (False, 2, 2048, 4), (False, 2, 300, 2),
                                                      (True, 2, 2048, 1), (True, 2, 2048, 4), (True, 2, 300, 2),
-                                                     (True, 3, 1000, 3), (True, 80, 640, 1), (True, 1, 128, 1)])
+                                                     (True, 3, 1000, 3), (True, 80, 640, 1), (True, 1, 128, 1),
+                                                     (True, 2, 1024, -1), (False, 2, 1024, -1)])
 def test_pool_attention(cuda, monkeypatch, tensor_cores, B, N, splits):
     """mma.sync kernel and tcgen05 / TMEM kernel (key splits + combine, ragged last tile, several items per warpgroup)
     against torch SDPA.  Padding rows hold finite non-zero keys / values that must be masked out."""
@@ -248,6 +249,11 @@ def test_pool_attention(cuda, monkeypatch, tensor_cores, B, N, splits):
     g = _gen(6)
     kv = torch.full((B, Np, 3 * C), 3.0)
     kv[:, :N] = torch.randn(B, N, 3 * C, generator=g)
+    if splits < 0:
+        # keys growing along the cloud: the running maximum of the scores jumps by hundreds between tiles (the
+        # single-pass softmax of the tcgen05 kernel must fall back to moving its reference first)
+        splits = 1
+        kv[:, :N, :C] *= (1.0 + torch.arange(N) / 16.0)[None, :, None]
     ind = torch.randn(1, H, I, D, generator=g)
     kvd = kv.to(cuda).bfloat16().reshape(B * Np, 3 * C)
     qs = (ind[0] * (D**-0.5 * math.log2(math.e))).to(cuda).bfloat16().contiguous()
@@ -257,7 +263,10 @@ def test_pool_attention(cuda, monkeypatch, tensor_cores, B, N, splits):
     kvr = kvd.float().cpu().view(B, Np, 3 * C)[:, :N]
     k = kvr[..., :C].reshape(B, N, H, D).transpose(1, 2)
     v = kvr[..., C:2 * C].reshape(B, N, H, D).transpose(1, 2)
-    ref = F.scaled_dot_product_attention(ind.expand(B, -1, -1, -1), k, v).transpose(1, 2).reshape(B, I, C)
+    # queries as the kernel sees them (bf16-rounded after the scale fold): with logits in the hundreds the rounding of
+    # the queries alone moves the softmax
+    qr = (qs.float().cpu() / (D**-0.5 * math.log2(math.e)))[None]
+    ref = F.scaled_dot_product_attention(qr.expand(B, -1, -1, -1), k, v).transpose(1, 2).reshape(B, I, C)
     err = (out.float().cpu().view(B, I, C) - ref).abs().max().item()
     assert err < 2e-2, err
 
