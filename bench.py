@@ -204,8 +204,11 @@ def run_own(args):
         value = clouds / (ms * 1e-3)
         traffic = None
         tfile = ROOT / "profiles" / "roofline_traffic.json"
+        lookup_traffic = None
         if tfile.exists():
-            traffic = json.loads(tfile.read_text()).get("gemm_dram_bytes_per_launch")
+            tj = json.loads(tfile.read_text())
+            traffic = tj.get("gemm_dram_bytes_per_launch")
+            lookup_traffic = tj.get("lookup_dram_bytes_per_launch")
         line = {
             "metric": "point clouds/sec (2048 pts, full EDM sampler)", "value": value, "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -230,7 +233,10 @@ def run_own(args):
                          "whole_path_frac_of_tensor_peak": B * EVALS * FLOP_PER_EVAL * args.steps / (ms * 1e-3) / 1e12 / pk["tf_sustained"],
                          "lookup_hbm": None if look is None else {
                              "achieved_gbs": look["bytes"] / (look["ms"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
-                             "frac": look["bytes"] / (look["ms"] * 1e-3) / 1e9 / pk["hbm"]}},
+                             "frac": look["bytes"] / (look["ms"] * 1e-3) / 1e9 / pk["hbm"],
+                             "kernel": "lookup_staged_kernel (shared-memory staged pyramid slices); algorithmic bytes = "
+                                       "pyramid + bf16 output + coordinates per launch",
+                             "us_per_launch": look["ms"] * 1e3 / look["launches"], "traffic": lookup_traffic}},
             "kernel_classes": [{"name": p["name"], "launches": p["launches"], "ms": round(p["ms"], 3),
                                 "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["ms"] > 0 else None,
                                 "gbs": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1) if p["ms"] > 0 else None} for p in prof],
