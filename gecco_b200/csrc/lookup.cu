@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
 
   // geometry of this slice: 16 B units per pixel, byte offset of every level in shared memory, thread units per point
   int nU[GECCO_MAX_LEVELS], sm_off[GECCO_MAX_LEVELS], col_off[GECCO_MAX_LEVELS];
-  int off = 0, tpp = 0, col = 0;
+  int off = LS_SGRP_BYTES, tpp = 0, col = 0;  // [per-group sums][pyramid slice][tap tables]
 #pragma unroll
   for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
     nU[l] = l < p.n_levels ? p.lvl_c[l] / (8 * S) : 0;
@@ -307,12 +307,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
     tpp += nU[l] / UPT;
     col += p.lvl_c[l];
   }
-  double* sgrp = reinterpret_cast<double*>(lsm + off);
+  double* sgrp = reinterpret_cast<double*>(lsm);
   // two tap tables (chunk parity): [n_levels][LS_CHUNK] 4 x u16 pixel indices, then [n_levels][LS_CHUNK] 4 weights
   const int tab_bytes = p.n_levels * LS_CHUNK * 24;
-  uint8_t* tab0 = lsm + off + LS_SGRP_BYTES;
-  double* csum = reinterpret_cast<double*>(tab0);  // after the point loop: per-column sums [ctot][2] (double: the
-                                                   // shared-memory atomics arrive in any order)
+  uint8_t* tab0 = lsm + off;
 
   // ---- stage the slice (asynchronously; the tap table of the first chunk is computed under it)
 #pragma unroll
@@ -483,29 +481,39 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
     __syncthreads();
   }
 
-  // ---- GroupNorm statistics (models/ray.py:53): per-column sums -> per-group sums -> global accumulators
+  // ---- GroupNorm statistics (models/ray.py:53).  Deterministic: every thread parks its per-column sums in shared memory
+  // (the pyramid slice is no longer needed), one thread per column adds the point lanes in a fixed order, and only the
+  // per-group / global accumulation uses (double) atomics.
   if (p.stats != nullptr) {
-    for (int i = tid; i < p.ctot * 2; i += LS_THREADS) csum[i] = 0.0;
+    float* red = reinterpret_cast<float*>(lsm + LS_SGRP_BYTES);  // [2][lanes][ctot]
     for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS) sgrp[i] = 0.0;
-    __syncthreads();
     if (active) {
 #pragma unroll
       for (int k = 0; k < UPT; ++k)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          double* c = csum + (my_col + k * kcol + j) * 2;
-          atomicAdd(c + 0, static_cast<double>(s1[k][j]));
-          atomicAdd(c + 1, static_cast<double>(s2[k][j]));
+          red[pl * p.ctot + my_col + k * kcol + j] = s1[k][j];
+          red[(lanes + pl) * p.ctot + my_col + k * kcol + j] = s2[k][j];
         }
     }
     __syncthreads();
     const int gsz = p.ctot / p.stat_groups;
     for (int i = tid; i < p.ctot; i += LS_THREADS) {
-      const double a = csum[i * 2], b = csum[i * 2 + 1];
-      if (a != 0.0 || b != 0.0) {  // columns of other slices stay zero
-        atomicAdd(&sgrp[(i / gsz) * 2], a);
-        atomicAdd(&sgrp[(i / gsz) * 2 + 1], b);
+      // column i belongs to this slice if it lies in [slice C_l / S, (slice + 1) C_l / S) of its level
+      bool mine = false;
+#pragma unroll
+      for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
+        const int c = i - col_off[l];
+        if (nU[l] > 0 && c >= 0 && c < p.lvl_c[l]) mine = c / (nU[l] * 8) == slice;
       }
+      if (!mine) continue;
+      double a = 0.0, b = 0.0;
+      for (int q = 0; q < lanes; ++q) {
+        a += static_cast<double>(red[q * p.ctot + i]);
+        b += static_cast<double>(red[(lanes + q) * p.ctot + i]);
+      }
+      atomicAdd(&sgrp[(i / gsz) * 2], a);
+      atomicAdd(&sgrp[(i / gsz) * 2 + 1], b);
     }
     __syncthreads();
     for (int i = tid; i < p.stat_groups * 2; i += LS_THREADS)
@@ -549,9 +557,12 @@ StagedPlan plan_staged(const LookupP& p, int stat_groups) {
     if (!ok) continue;
     const int upt = even ? 2 : 1;
     if (units / upt > LS_THREADS) continue;
-    size_t tab = (size_t)2 * p.n_levels * LS_CHUNK * 24;  // two tap tables
-    if ((size_t)p.ctot * 16 > tab) tab = (size_t)p.ctot * 16;  // per-column sums alias the tables
-    const size_t total = bytes + LS_SGRP_BYTES + tab;
+    const size_t tab = (size_t)2 * p.n_levels * LS_CHUNK * 24;  // two tap tables
+    // the statistics epilogue reuses the slice + tables for [2][point lanes][ctot] floats
+    const size_t red = (size_t)2 * (LS_THREADS / (units / upt)) * p.ctot * 4;
+    size_t total = bytes + tab;
+    if (red > total) total = red;
+    total += LS_SGRP_BYTES;
     if (total > LS_SMEM_MAX) continue;
     return {S, upt, total};
   }
