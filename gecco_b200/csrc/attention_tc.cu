@@ -310,6 +310,8 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ vt) {
   constexpr int CH = C / 2;
   __shared__ __nv_bfloat16 tile[NI][CH + 8];
+  pdl_wait();  // programmatic dependent launch: the predecessor has completed
+  pdl_launch_dependents();
   const int cloud = blockIdx.x, c0 = blockIdx.y * CH;
   const __nv_bfloat16* src = kv + (long long)cloud * NI * ldkv + v_off + c0;
   for (int i = threadIdx.x; i < NI * (CH / 8); i += blockDim.x) {
@@ -340,7 +342,7 @@ int launch_unpool_tc(const gecco_unpool_args& a, cudaStream_t stream) {
   GECCO_REQUIRE(unpool_tc_supported(a), "unpool attention (tcgen05): unsupported shape");
   const long long rows = (long long)a.clouds * a.rows_per_cloud;
   __nv_bfloat16* vt = static_cast<__nv_bfloat16*>(a.vt_scratch);
-  transpose_v_kernel<<<dim3(a.clouds, 2), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.kv), a.ldkv, a.v_off, vt);
+  launch_pdl(transpose_v_kernel, dim3(a.clouds, 2), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(a.kv), a.ldkv, a.v_off, vt);
   GECCO_CHECK_LAUNCH("transpose_v_kernel");
 
   CUtensorMap tq, tk, tvt, ty;

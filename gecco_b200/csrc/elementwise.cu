@@ -76,6 +76,8 @@ __global__ void adagn_apply_kernel(const float* __restrict__ x, long long ldx, c
                                    int rows_per_cloud, int valid_rows, int C, int groups, float eps,
                                    __nv_bfloat16* __restrict__ out16, long long ldo16, float* __restrict__ out32,
                                    long long ldo32) {
+  pdl_wait();  // programmatic dependent launch: the predecessor has completed
+  pdl_launch_dependents();
   const int cloud = blockIdx.y;
   const int r0 = blockIdx.x * ADAGN_ROWS;
   const int gs = C / groups;
@@ -149,6 +151,8 @@ fold_adagn_kernel(const float* __restrict__ W, long long ldw, const float* __res
                   const float* __restrict__ scale_b, const float* __restrict__ bias_w, const float* __restrict__ bias_b,
                   int clouds, __nv_bfloat16* __restrict__ wf, long long ldwf, long long wf_cloud_stride,
                   float* __restrict__ bf, int bf_stride) {
+  pdl_wait();  // programmatic dependent launch: the predecessor has completed
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float fold_smem[];
   float* sa = fold_smem;                      // [FOLD_CLOUDS][C]
   float* ss = sa + FOLD_CLOUDS * C;           // [FOLD_CLOUDS][C]
@@ -336,6 +340,8 @@ __device__ __forceinline__ void head_finish(const gecco_head_args& a, long long 
 template <int NQ>
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 head_kernel(const gecco_head_args a) {
+  pdl_wait();  // programmatic dependent launch: the predecessor has completed
+  pdl_launch_dependents();
   extern __shared__ float smem_head[];  // [groups][2] mean, rstd (GroupNorm mode)
   const int cloud = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -528,10 +534,9 @@ int launch_adagn(const gecco_adagn_args& a, cudaStream_t s) {
   GECCO_REQUIRE(a.ldx % 4 == 0 && (!a.out_bf16 || a.ldo16 % 4 == 0) && (!a.out_f32 || a.ldo32 % 4 == 0), "adagn: bad leading dimension");
   dim3 grid(ceil_div(a.rows_per_cloud, ADAGN_ROWS), a.clouds);
   const int threads = a.c / 4 < 256 ? ((a.c / 4 + 31) / 32) * 32 : 256;
-  adagn_apply_kernel<<<grid, threads, 0, s>>>(a.x, a.ldx, a.stats, a.stat_gs, a.t, a.t_stride, a.ctx_dim, a.scale_w,
-                                             a.scale_b, a.bias_w, a.bias_b, a.rows_per_cloud, a.valid_rows, a.c,
-                                             a.groups, a.eps, static_cast<__nv_bfloat16*>(a.out_bf16), a.ldo16,
-                                             a.out_f32, a.ldo32);
+  launch_pdl(adagn_apply_kernel, grid, dim3(threads), 0, s, a.x, a.ldx, a.stats, a.stat_gs, a.t, a.t_stride, a.ctx_dim, a.scale_w,
+             a.scale_b, a.bias_w, a.bias_b, a.rows_per_cloud, a.valid_rows, a.c, a.groups, a.eps,
+             static_cast<__nv_bfloat16*>(a.out_bf16), a.ldo16, a.out_f32, a.ldo32);
   GECCO_CHECK_LAUNCH("adagn_apply_kernel");
   return GECCO_OK;
 }
@@ -546,10 +551,9 @@ int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s) {
   if (a.n_out == 0 || a.clouds == 0) return GECCO_OK;
   dim3 grid(ceil_div(a.n_out, FOLD_ROWS), ceil_div(a.clouds, FOLD_CLOUDS));
   const size_t smem = (size_t)FOLD_CLOUDS * (2 * a.c + 2 * a.groups) * sizeof(float);
-  fold_adagn_kernel<<<grid, FOLD_THREADS, smem, s>>>(a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
-                                        (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b,
-                                        a.bias_w, a.bias_b, a.clouds, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf,
-                                        a.wf_cloud_stride, a.bias_folded, a.bias_stride);
+  launch_pdl(fold_adagn_kernel, grid, dim3(FOLD_THREADS), smem, s, a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
+             (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b, a.bias_w, a.bias_b,
+             a.clouds, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf, a.wf_cloud_stride, a.bias_folded, a.bias_stride);
   GECCO_CHECK_LAUNCH("fold_adagn_kernel");
   return GECCO_OK;
 }
@@ -580,7 +584,7 @@ int launch_head(const gecco_head_args& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.valid_rows, HEAD_WARPS * HEAD_ROWS_PER_WARP), a.clouds);
   const size_t sm = a.norm == 2 ? a.groups * 2 * sizeof(float) : 0;
   switch (a.c / 128) {
-#define GECCO_HEAD_CASE(NQ) case NQ: head_kernel<NQ><<<grid, HEAD_WARPS * 32, sm, s>>>(a); break;
+#define GECCO_HEAD_CASE(NQ) case NQ: launch_pdl(head_kernel<NQ>, grid, dim3(HEAD_WARPS * 32), sm, s, a); break;
     GECCO_HEAD_CASE(1) GECCO_HEAD_CASE(2) GECCO_HEAD_CASE(3) GECCO_HEAD_CASE(4)
     GECCO_HEAD_CASE(5) GECCO_HEAD_CASE(6) GECCO_HEAD_CASE(7) GECCO_HEAD_CASE(8)
 #undef GECCO_HEAD_CASE

@@ -95,6 +95,8 @@ __global__ void scale_add_f32_kernel(const float* __restrict__ a, const float* _
 __global__ void prep_kernel(double* __restrict__ stats, long long n_stats, const float* __restrict__ sigma, int stride,
                             float sigma_imm, const float* __restrict__ t_embed, int t_stride, int clouds,
                             float* __restrict__ sigma_eff, float* __restrict__ c_noise) {
+  pdl_wait();  // programmatic dependent launch: the predecessor (the previous evaluation's head) has completed
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long j = i; j < n_stats; j += (long long)gridDim.x * blockDim.x) stats[j] = 0.0;
   if (i < clouds) {
@@ -289,8 +291,8 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     if (blocks > 1024) blocks = 1024;
     if ((long long)blocks * threads < clouds) blocks = ceil_div(clouds, threads);
     prof_begin(K_PREP, 0, 8.0 * w.n_stats, s);
-    prep_kernel<<<blocks, threads, 0, s>>>(w.stats, w.n_stats, sigma, sigma_stride, sigma_imm, t_embed, t_stride, clouds,
-                                           w.sigma_eff, w.c_noise);
+    launch_pdl(prep_kernel, dim3(blocks), dim3(threads), 0, s, w.stats, w.n_stats, sigma, sigma_stride, sigma_imm, t_embed, t_stride,
+               clouds, w.sigma_eff, w.c_noise);
     prof_end(s);
     GECCO_CHECK_LAUNCH("prep_kernel");
   }

@@ -291,6 +291,8 @@ __device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {
 template <int UPT, bool PACKED>
 __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const LookupP p, const int S, const int pts_per_cta) {
   extern __shared__ __align__(16) uint8_t lsm[];
+  pdl_wait();  // programmatic dependent launch: the predecessor has completed
+  pdl_launch_dependents();
   const int slice = blockIdx.x, cloud = blockIdx.y, tid = threadIdx.x;
   const int pt_begin = blockIdx.z * pts_per_cta;
   const int pt_end = min(p.points, pt_begin + pts_per_cta);
@@ -578,6 +580,8 @@ fold_gn_kernel(const float* __restrict__ W, const float* __restrict__ bias, cons
                float eps, int groups, int c_in, int c_out, __nv_bfloat16* __restrict__ wb, long long ldwb,
                float* __restrict__ bb) {
   __shared__ float smean[64], srstd[64];
+  pdl_wait();  // programmatic dependent launch: the predecessor has completed
+  pdl_launch_dependents();
   const int cloud = blockIdx.y;
   const int gs = c_in / groups;
   const double* cs = stats + (long long)cloud * groups * 2;
@@ -676,7 +680,7 @@ int launch_lookup(const gecco_lookup_args& a, cudaStream_t s) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM_MAX);
         done = true;
       }
-      kern<<<grid, LS_THREADS, plan.smem, s>>>(p, plan.S, per);
+      launch_pdl(kern, grid, dim3(LS_THREADS), plan.smem, s, p, plan.S, per);
     };
     static bool attr_done[4] = {false, false, false, false};
     if (plan.upt == 2 && packed) go(lookup_staged_kernel<2, true>, attr_done[0]);
@@ -702,8 +706,8 @@ int launch_fold_gn(const float* W, const float* bias, const double* stats, doubl
                    int c_in, int c_out, int clouds, void* wb, long long ldwb, float* bb, cudaStream_t s) {
   GECCO_REQUIRE(groups > 0 && groups <= 64 && c_in % groups == 0 && c_in % 2 == 0 && ldwb % 2 == 0, "fold_gn: bad layout");
   dim3 grid(ceil_div(c_out, FGN_ROWS), clouds);
-  fold_gn_kernel<<<grid, 128, 0, s>>>(W, bias, stats, count, eps, groups, c_in, c_out,
-                                      static_cast<__nv_bfloat16*>(wb), ldwb, bb);
+  launch_pdl(fold_gn_kernel, grid, dim3(128), 0, s, W, bias, stats, count, eps, groups, c_in, c_out, static_cast<__nv_bfloat16*>(wb),
+             ldwb, bb);
   GECCO_CHECK_LAUNCH("fold_gn_kernel");
   return GECCO_OK;
 }
