@@ -12,8 +12,9 @@
 //     starting at column 48h of k.
 //   * one thread per stacked row: running max / sum over the tiles (flash-attention recurrence, base-2 exponentials),
 //     P = exp2(S - m) written as bf16 into two swizzled K-major k-blocks (points contiguous).
-//   * O_a = P V_h, O_b = P V_h+1 : 2 x eight M128 N48 K16 MMAs with V as the MN-major B operand, i.e. exactly the
-//     [point][channel] window TMA delivers (no transpose anywhere); the products land in the TMEM columns S occupied.
+//   * O = P [V_h | V_h+1] : eight M128 N96 K16 MMAs with the pair's v columns as the MN-major B operand, i.e. exactly the
+//     [point][channel] boxes TMA delivers (no transpose anywhere; the second 64-channel atom is the next box, LBO);
+//     rows of head h use columns 0-47 of O, rows of head h+1 columns 48-95; O lands in TMEM columns S occupied.
 //     The thread rescales its 48 fp32 accumulators in registers: acc = acc * 2^(m_old - m_new) + O.
 //   * end of an item: the normalised bf16 row ("b h i d -> b i (h d)") when the item covers all keys, else the
 //     (acc, m, l) partial for pool_combine_kernel.
@@ -50,6 +51,16 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 // kind::f16 instruction descriptor with B MN-major (bit 16): bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 16); }
+// MN-major, 128B-swizzled B operand spanning two 64-element atoms `lbo_bytes` apart (8-row K groups 1024 B apart).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 struct PParams {
   const __nv_bfloat16* q_ind;  // [8][64][48], pre-scaled
@@ -177,7 +188,9 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
           if (cur[w].done()) continue;
           const int row = cur[w].cloud * p.rows_per_cloud + cur[w].tile * TM;
           for (int j = 0; j < 2; ++j) {
-            const int col = (2 * cur[w].pair + j) * HD;  // columns past 384 are zero-filled
+            // K: the window of head 2 pair + j; V: the two 64-column boxes of the pair's 96 channels.  Columns past 384
+            // are zero-filled.
+            const int col = kind == 0 ? (2 * cur[w].pair + j) * HD : cur[w].pair * 2 * HD + j * 64;
             if (kind == 0) {
               const uint32_t slot = gk % SLOTS, use = gk / SLOTS;
               mbar_wait(&k_empty[slot], (use & 1u) ^ 1u);
@@ -201,7 +214,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
   } else if (uwarp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     constexpr uint32_t idesc_s = umma_idesc_bf16(TM, TM);          // M = 128 stacked rows, N = 128 points
-    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(TM, HD);      // M = 128 stacked rows, N = 48 channels (MN-major V)
+    constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(TM, 2 * HD);  // M = 128 stacked rows, N = 96 channels (MN-major V)
     const uint32_t sQ_u = uniform_u32(smem_u32(sQ)), sK_u = uniform_u32(smem_u32(sK)), sV_u = uniform_u32(smem_u32(sV));
     const uint32_t sP_u = uniform_u32(smem_u32(sP));
     const uint32_t tmem_u = uniform_u32(tmem_base);
@@ -250,16 +263,15 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
       mbar_wait(&v_full[v1], ((gv + 1) / SLOTS) & 1u);
       tc_fence_after_sync();
       if (elect_one()) {
+        // one product for both heads: N = the pair's 96 channels (two adjacent 64-channel boxes, the second atom one
+        // window further: LBO); rows of head h use columns 0-47 of O, rows of head h+1 columns 48-95
+        const uint32_t vb = sV_u + v0 * WIN_BYTES;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const uint32_t vb = sV_u + (hh ? v1 : v0) * WIN_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < TM / 16; ++kk) {
-            // A: P, K-major, k-block kk / 4 (64 points), 16-point slice kk % 4.  B: V window, MN-major: 16 points = 2048 B.
-            const uint64_t da = umma_desc_k_sw128(sP_u + w * P_BYTES + (kk >> 2) * (TM * 128)) + 2 * (kk & 3);
-            const uint64_t db = umma_desc_k_sw128(vb + kk * 2048);
-            umma_bf16_ss(tmem_u + w * 256 + hh * 128, da, db, idesc_o, kk ? 1u : 0u);
-          }
+        for (int kk = 0; kk < TM / 16; ++kk) {
+          // A: P, K-major, k-block kk / 4 (64 points), 16-point slice kk % 4.  B: V boxes, MN-major: 16 points = 2048 B.
+          const uint64_t da = umma_desc_k_sw128(sP_u + w * P_BYTES + (kk >> 2) * (TM * 128)) + 2 * (kk & 3);
+          const uint64_t db = umma_desc_mn_sw128(vb + kk * 2048, WIN_BYTES);
+          umma_bf16_ss(tmem_u + w * 256, da, db, idesc_o, kk ? 1u : 0u);
         }
         umma_commit(&v_empty[v0]);
         umma_commit(&v_empty[v1]);
@@ -288,6 +300,7 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
     const uint32_t row = q * 32 + lane;           // stacked row: head 2 pair + (row >> 6), inducer row & 63
     const uint32_t x7 = (row & 7u) << 4;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * 256 + (q >> 1) * 128;
+    const uint32_t o_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * 256 + (q >> 1) * HD;  // this row's O
     const uint32_t p_row = smem_u32(sP) + w * P_BYTES + row * 128u;
     Cursor& c = cur[w];
     uint32_t n = 0;  // units processed
@@ -394,9 +407,9 @@ pool_tc_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant_
       tc_fence_after_sync();
       {
         uint32_t o[HD];
-        tmem_ld16(t_addr, o);
-        tmem_ld16(t_addr + 16, o + 16);
-        tmem_ld16(t_addr + 32, o + 32);
+        tmem_ld16(o_addr, o);
+        tmem_ld16(o_addr + 16, o + 16);
+        tmem_ld16(o_addr + 32, o + 32);
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
