@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace gecco {
 
 namespace {
@@ -222,6 +224,106 @@ fold_adagn_kernel(const float* __restrict__ W, long long ldw, const float* __res
       for (int cl = 0; cl < FOLD_CLOUDS; ++cl) {
         const float d = warp_sum(dot[u][cl]);
         if (lane == 0 && o < o_end && cl < ncl) bf[(long long)(cloud0 + cl) * bf_stride + o] = d + b0;
+      }
+    }
+  }
+}
+
+// Same fold, specialised for C = 128 NSTEP (384 on this path) with the weight rows held in registers: a warp owns
+// FOLD_ROWS / 8 = 6 rows in two halves of 3; the 9 float4 loads of a half are issued together, the first half BEFORE the
+// prologue (the weights do not depend on the statistics), so the L2 latency of the weights is paid twice per warp under
+// other work instead of nine times in sequence as in the generic kernel (24 -> see DESIGN.md for the measured time).
+template <int NSTEP>
+__global__ void __launch_bounds__(FOLD_THREADS, 2)
+fold_adagn_fast_kernel(const float* __restrict__ W, long long ldw, const float* __restrict__ bias, int n_out,
+                       const double* __restrict__ stats, int stat_gs, int groups, double count, float eps,
+                       const float* __restrict__ t, int t_stride, const float* __restrict__ scale_w,
+                       const float* __restrict__ scale_b, const float* __restrict__ bias_w, const float* __restrict__ bias_b,
+                       int clouds, __nv_bfloat16* __restrict__ wf, long long ldwf, long long wf_cloud_stride,
+                       float* __restrict__ bf, int bf_stride) {
+  constexpr int C = 128 * NSTEP;
+  constexpr int NW = FOLD_THREADS / 32;
+  constexpr int HALF = FOLD_ROWS / NW / 2;  // 3 rows per half
+  extern __shared__ __align__(16) float fold_smem[];
+  float* sa = fold_smem;                      // [FOLD_CLOUDS][C]
+  float* ss = sa + FOLD_CLOUDS * C;           // [FOLD_CLOUDS][C]
+  float* smean = ss + FOLD_CLOUDS * C;        // [FOLD_CLOUDS][groups]
+  float* srstd = smean + FOLD_CLOUDS * groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cloud0 = blockIdx.y * FOLD_CLOUDS;
+  const int ncl = min(FOLD_CLOUDS, clouds - cloud0);
+  const int row0 = blockIdx.x * FOLD_ROWS + warp;  // rows row0 + NW i, i < 6
+  auto load_half = [&](int h, float4 (&w)[HALF][NSTEP]) {
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      const int o = row0 + (h * HALF + i) * NW;
+#pragma unroll
+      for (int j = 0; j < NSTEP; ++j)
+        w[i][j] = o < n_out ? __ldg(reinterpret_cast<const float4*>(W + (long long)o * ldw + lane * 4 + 128 * j))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 w[HALF][NSTEP];
+  load_half(0, w);  // weights are constants: in flight across the wait on the predecessor and the prologue
+  pdl_wait();       // programmatic dependent launch: the predecessor (producer of the statistics) has completed
+  pdl_launch_dependents();
+  const int gs = C / groups;
+  for (int i = threadIdx.x; i < ncl * groups; i += blockDim.x) {
+    const int cl = i / groups, g = i - cl * groups;
+    float mean, rstd;
+    group_mean_rstd(stats + (long long)(cloud0 + cl) * (C / stat_gs) * 2, g, gs, stat_gs, count, eps, mean, rstd);
+    smean[i] = mean;
+    srstd[i] = rstd;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncl * C; i += blockDim.x) {
+    const int cl = i / C, c = i - cl * C;
+    const int g = c / gs;
+    const float tc = __ldg(t + (long long)(cloud0 + cl) * t_stride);
+    const float sc = tc * __ldg(scale_w + c) + __ldg(scale_b + c);
+    const float bi = tc * __ldg(bias_w + c) + __ldg(bias_b + c);
+    const float a = sc * srstd[cl * groups + g];
+    sa[i] = a;
+    ss[i] = bi - a * smean[cl * groups + g];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (h == 1) load_half(1, w);
+    float dot[HALF][FOLD_CLOUDS];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i)
+#pragma unroll
+      for (int cl = 0; cl < FOLD_CLOUDS; ++cl) dot[i][cl] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NSTEP; ++j) {
+      const int c = lane * 4 + 128 * j;
+#pragma unroll
+      for (int cl = 0; cl < FOLD_CLOUDS; ++cl) {
+        if (cl >= ncl) break;
+        const float4 a = *reinterpret_cast<const float4*>(sa + cl * C + c);
+        const float4 sv = *reinterpret_cast<const float4*>(ss + cl * C + c);
+        __nv_bfloat16* dst = wf + (long long)(cloud0 + cl) * wf_cloud_stride + c;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+          const int o = row0 + (h * HALF + i) * NW;
+          if (o < n_out) {
+            const float4 wv = w[i][j];
+            dot[i][cl] += wv.x * sv.x + wv.y * sv.y + wv.z * sv.z + wv.w * sv.w;
+            *reinterpret_cast<uint2*>(dst + (long long)o * ldwf) =
+                make_uint2(pack_bf16x2(wv.x * a.x, wv.y * a.y), pack_bf16x2(wv.z * a.z, wv.w * a.w));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      const int o = row0 + (h * HALF + i) * NW;
+      const float b0 = (bias != nullptr && o < n_out) ? __ldg(bias + o) : 0.f;
+#pragma unroll
+      for (int cl = 0; cl < FOLD_CLOUDS; ++cl) {
+        const float d = warp_sum(dot[i][cl]);
+        if (lane == 0 && o < n_out && cl < ncl) bf[(long long)(cloud0 + cl) * bf_stride + o] = d + b0;
       }
     }
   }
@@ -551,6 +653,17 @@ int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s) {
   if (a.n_out == 0 || a.clouds == 0) return GECCO_OK;
   dim3 grid(ceil_div(a.n_out, FOLD_ROWS), ceil_div(a.clouds, FOLD_CLOUDS));
   const size_t smem = (size_t)FOLD_CLOUDS * (2 * a.c + 2 * a.groups) * sizeof(float);
+  static const bool fast_ok = [] {  // GECCO_FOLD_FAST=0: the generic kernel (A/B measurements)
+    const char* v = getenv("GECCO_FOLD_FAST");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  if (fast_ok && a.c == 384) {
+    launch_pdl(fold_adagn_fast_kernel<3>, grid, dim3(FOLD_THREADS), smem, s, a.w, a.ldw, a.bias, a.n_out, a.stats, a.stat_gs, a.groups,
+               (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b, a.bias_w, a.bias_b,
+               a.clouds, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf, a.wf_cloud_stride, a.bias_folded, a.bias_stride);
+    GECCO_CHECK_LAUNCH("fold_adagn_fast_kernel");
+    return GECCO_OK;
+  }
   launch_pdl(fold_adagn_kernel, grid, dim3(FOLD_THREADS), smem, s, a.w, a.ldw, a.bias, a.n_out, a.c, a.stats, a.stat_gs, a.groups,
              (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b, a.bias_w, a.bias_b,
              a.clouds, static_cast<__nv_bfloat16*>(a.w_folded_bf16), a.ldwf, a.wf_cloud_stride, a.bias_folded, a.bias_stride);
