@@ -653,10 +653,8 @@ int launch_fold_adagn(const gecco_fold_adagn_args& a, cudaStream_t s) {
   if (a.n_out == 0 || a.clouds == 0) return GECCO_OK;
   dim3 grid(ceil_div(a.n_out, FOLD_ROWS), ceil_div(a.clouds, FOLD_CLOUDS));
   const size_t smem = (size_t)FOLD_CLOUDS * (2 * a.c + 2 * a.groups) * sizeof(float);
-  static const bool fast_ok = [] {  // GECCO_FOLD_FAST=0: the generic kernel (A/B measurements)
-    const char* v = getenv("GECCO_FOLD_FAST");
-    return !(v != nullptr && v[0] == '0');
-  }();
+  const char* ffv = getenv("GECCO_FOLD_FAST");  // GECCO_FOLD_FAST=0: the generic kernel (A/B measurements, tests)
+  const bool fast_ok = !(ffv != nullptr && ffv[0] == '0');
   if (fast_ok && a.c == 384) {
     launch_pdl(fold_adagn_fast_kernel<3>, grid, dim3(FOLD_THREADS), smem, s, a.w, a.ldw, a.bias, a.n_out, a.stats, a.stat_gs, a.groups,
                (double)a.valid_rows * (a.c / a.groups), a.eps, a.t, a.t_stride, a.scale_w, a.scale_b, a.bias_w, a.bias_b,

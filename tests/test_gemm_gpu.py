@@ -125,12 +125,15 @@ def test_gemm_persistent_residual_inplace(cuda, m, n, k):
         assert torch.allclose(stats[..., 1], (v * v).sum(dim=(1, 3)), rtol=1e-4, atol=5e-2)
 
 
-def test_fold_adagn_matches_adagn_then_linear(cuda):
-    """AdaGN -> Linear folded into per-cloud weights (gecco_fold_adagn) + per-cloud GEMM on the raw stream
-    == Linear(AdaGN(x)) (models/normalization.py:36-44)."""
+@pytest.mark.parametrize("fast,B,O", [("1", 3, 1152), ("0", 3, 1152), ("1", 5, 776), ("0", 5, 776)])
+def test_fold_adagn_matches_adagn_then_linear(cuda, monkeypatch, fast, B, O):
+    """AdaGN -> Linear folded into per-cloud weights (gecco_fold_adagn: the register-prefetching C = 384 kernel and the
+    generic one; cloud groups and row blocks with tails) + per-cloud GEMM on the raw stream == Linear(AdaGN(x))
+    (models/normalization.py:36-44)."""
     from gecco_b200 import ops
 
-    B, N, Np, C, O = 3, 200, 256, 384, 1152
+    monkeypatch.setenv("GECCO_FOLD_FAST", fast)
+    N, Np, C = 200, 256, 384
     g = torch.Generator(device="cpu").manual_seed(21)
     x = (torch.randn(B, Np, C, generator=g) * 1.7 + 0.3).to(cuda)
     x[:, N:] = 0
