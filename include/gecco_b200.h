@@ -42,6 +42,10 @@ int gecco_init(int device);
 int gecco_set_option(const char* name, int value);
 /* Development aid: device buffer ([148][16] int64) receiving per-CTA cycle counters of the CTA-pair GEMM; NULL disables. */
 int gecco_set_debug_buffer(void* buf);
+/* Development aid (tools/umma_bench.py): cycles for `batch` back-to-back M128 x n x K16 bf16 tcgen05.mma on one SM.
+ * mode 0: A, B from shared memory (K-major); 1: B MN-major; 2: A from TMEM, B K-major; 3: A from TMEM, B MN-major.
+ * out: device buffer of two int64 (best, mean over reps - 1 repetitions). */
+int gecco_debug_umma_bench(int32_t mode, int32_t n, int32_t batch, int32_t reps, long long* out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Dense projection on the tcgen05 tensor cores.
