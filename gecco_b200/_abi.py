@@ -242,6 +242,8 @@ def load() -> C.CDLL:
     lib.gecco_destroy.argtypes = [C.c_void_p]
     lib.gecco_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gecco_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gecco_graph_status.argtypes = [C.c_void_p]
+    lib.gecco_graph_status.restype = C.c_int
     _lib = lib
     return lib
 

@@ -740,6 +740,42 @@ extern "C" int gecco_head(const gecco_head_args* a, void* stream) {
   return gecco::launch_head(*a, static_cast<cudaStream_t>(stream));
 }
 
+namespace gecco {
+namespace {
+// GaussianActivation (models/activation.py:17-24) as a stand-alone op: y = exp(-x^2 / (2 alpha^2)), optionally
+// (y - 0.7) / 0.28.  On the hot path the activation lives in the epilogue of the GEMM that produces x.
+__global__ void gaussian_act_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float k, int normalized) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    float4 o;
+    o.x = exp2f(v.x * v.x * k); o.y = exp2f(v.y * v.y * k); o.z = exp2f(v.z * v.z * k); o.w = exp2f(v.w * v.w * k);
+    if (normalized) { o.x = (o.x - 0.7f) / 0.28f; o.y = (o.y - 0.7f) / 0.28f; o.z = (o.z - 0.7f) / 0.28f; o.w = (o.w - 0.7f) / 0.28f; }
+    *reinterpret_cast<float4*>(y + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) {
+      float o = exp2f(x[j] * x[j] * k);
+      y[j] = normalized ? (o - 0.7f) / 0.28f : o;
+    }
+  }
+}
+}  // namespace
+}  // namespace gecco
+
+extern "C" int gecco_gaussian_activation(const float* x, float* y, int64_t n, float alpha, int32_t normalized, void* stream) {
+  using namespace gecco;
+  GECCO_REQUIRE(x != nullptr && y != nullptr && n >= 0, "gaussian_activation: null argument");
+  GECCO_REQUIRE(alpha != 0.f, "gaussian_activation: alpha must be non-zero");
+  GECCO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "gaussian_activation: buffers must be 16-byte aligned");
+  if (n == 0) return GECCO_OK;
+  const float k = static_cast<float>(-1.4426950408889634 / (2.0 * (double)alpha * (double)alpha));
+  const long long quads = (n + 3) / 4;
+  gaussian_act_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, k, normalized);
+  GECCO_CHECK_LAUNCH("gaussian_act_kernel");
+  return GECCO_OK;
+}
+
 extern "C" int gecco_reparam(const void* in, void* out, int32_t is_double, int32_t kind, int32_t to_data,
                              const float* mean, const float* sigma, float logit_scale, const float* K,
                              int32_t clouds, int32_t points_per_cloud, void* stream) {

@@ -71,6 +71,20 @@ struct gecco_engine {
   float* img_bias;  // img_feature_proj.1.bias + xyz_embed.bias (cond)
   void* arena;      // one allocation holding all packed tensors
   size_t arena_bytes;
+  // CUDA graphs of whole sampler loops (gecco_sample): captured once per distinct argument set, replayed afterwards.
+  // Captured and replayed on the engine's own stream, forked from / joined to the caller's stream with events, so that
+  // the legacy default stream (which cannot be captured) works too.
+  struct SampleGraph {
+    std::vector<unsigned char> key;
+    cudaGraphExec_t exec;
+    long long launches;  // kernel launches one replay performs
+    unsigned long long stamp;
+  };
+  std::vector<SampleGraph> graphs;
+  unsigned long long graph_clock = 0;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int last_graph_status = 0;  // 0: eager, 1: captured this call, 2: replayed, <0: capture failed (ran eagerly)
 };
 
 namespace gecco {
@@ -602,6 +616,11 @@ extern "C" int gecco_create(const gecco_model_desc* desc, const float* const* ne
 
 extern "C" int gecco_destroy(gecco_engine* e) {
   if (e == nullptr) return GECCO_OK;
+  if (e->gstream != nullptr) cudaStreamSynchronize(e->gstream);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  if (e->ev_fork != nullptr) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join != nullptr) cudaEventDestroy(e->ev_join);
+  if (e->gstream != nullptr) cudaStreamDestroy(e->gstream);
   cudaFree(e->arena);
   delete e;
   return GECCO_OK;
@@ -629,12 +648,20 @@ extern "C" int gecco_denoise(gecco_engine* e, const gecco_denoise_args* a, void*
                   a->cache_out, h, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* stream) {
-  GECCO_REQUIRE(a != nullptr, "gecco_sample: null args");
-  TRY(check_common(e, a->clouds, a->points, a->ctx, a->workspace, a->workspace_bytes));
-  GECCO_REQUIRE(a->num_steps >= 1 && a->host_t_steps && a->host_gamma, "gecco_sample: schedule missing");
-  GECCO_REQUIRE(a->latents && a->noise && a->x_out, "gecco_sample: latents / noise / output missing");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+namespace gecco {
+namespace {
+
+int g_graphs_enabled = -1;  // -1: from the environment (GECCO_GRAPHS, default on)
+bool graphs_enabled() {
+  if (g_graphs_enabled < 0) {
+    const char* v = getenv("GECCO_GRAPHS");
+    g_graphs_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return g_graphs_enabled != 0;
+}
+
+// Enqueues the whole sampler loop on `s` (also under stream capture: no host synchronisation, no allocation).
+int enqueue_sample(gecco_engine* e, const gecco_sample_args* a, cudaStream_t s) {
   const Workspace w = carve(e, a->clouds, a->points, a->workspace);
   const long long n3 = (long long)a->clouds * a->points * 3;
   const double* t = a->host_t_steps;
@@ -665,6 +692,100 @@ extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* s
   GECCO_CHECK_LAUNCH("copy_f64_kernel");
   return GECCO_OK;
 }
+
+// Everything a captured sampler graph depends on: shapes, schedule (baked into kernel arguments) and every pointer.
+std::vector<unsigned char> sample_key(const gecco_sample_args* a) {
+  std::vector<unsigned char> k;
+  auto put = [&](const void* p, size_t n) { k.insert(k.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+  put(&a->clouds, sizeof(int32_t)); put(&a->points, sizeof(int32_t)); put(&a->num_steps, sizeof(int32_t));
+  put(a->host_t_steps, sizeof(double) * (a->num_steps + 1));
+  put(a->host_gamma, sizeof(double) * a->num_steps);
+  put(&a->s_noise, sizeof(double));
+  put(&a->latents, sizeof(void*)); put(&a->noise, sizeof(void*)); put(&a->x_out, sizeof(void*));
+  put(&a->ctx, sizeof(gecco_context));
+  put(&a->workspace, sizeof(void*)); put(&a->workspace_bytes, sizeof(int64_t));
+  const int fused = fused_mlp_enabled() ? 1 : 0;
+  put(&fused, sizeof(int));
+  return k;
+}
+
+constexpr size_t kMaxSampleGraphs = 4;
+
+void drop_graph(gecco_engine* e, size_t i) {
+  cudaGraphExecDestroy(e->graphs[i].exec);
+  e->graphs.erase(e->graphs.begin() + i);
+}
+
+}  // namespace
+void set_graphs_option(int value) { g_graphs_enabled = value != 0 ? 1 : 0; }
+}  // namespace gecco
+
+extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* stream) {
+  GECCO_REQUIRE(a != nullptr, "gecco_sample: null args");
+  TRY(check_common(e, a->clouds, a->points, a->ctx, a->workspace, a->workspace_bytes));
+  GECCO_REQUIRE(a->num_steps >= 1 && a->host_t_steps && a->host_gamma, "gecco_sample: schedule missing");
+  GECCO_REQUIRE(a->latents && a->noise && a->x_out, "gecco_sample: latents / noise / output missing");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  e->last_graph_status = 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (s != nullptr && s != cudaStreamLegacy) cudaStreamIsCapturing(s, &cap);
+  if (!graphs_enabled() || g_prof.on || cap != cudaStreamCaptureStatusNone) return enqueue_sample(e, a, s);
+
+  if (e->gstream == nullptr) {
+    cudaError_t ce = cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
+    if (ce != cudaSuccess) return fail_cuda(ce, "gecco_sample: graph stream / events");
+  }
+  const std::vector<unsigned char> key = sample_key(a);
+  size_t hit = e->graphs.size();
+  for (size_t i = 0; i < e->graphs.size(); ++i)
+    if (e->graphs[i].key == key) { hit = i; break; }
+  if (hit == e->graphs.size()) {
+    // capture (thread-local mode: other threads' CUDA calls neither join nor invalidate it)
+    const long long before = g_launches;
+    cudaError_t ce = cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) return fail_cuda(ce, "gecco_sample: cudaStreamBeginCapture");
+    const int rc = enqueue_sample(e, a, e->gstream);
+    cudaGraph_t graph = nullptr;
+    ce = cudaStreamEndCapture(e->gstream, &graph);
+    const long long launches = g_launches - before;
+    g_launches = before;  // counted per replay below
+    cudaGraphExec_t exec = nullptr;
+    if (rc == GECCO_OK && ce == cudaSuccess && graph != nullptr) ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (rc != GECCO_OK) return rc;  // argument errors surface exactly as in the eager path
+    if (ce != cudaSuccess || exec == nullptr) {
+      // a driver that cannot capture this launch sequence: run eagerly, visibly (gecco_last_graph_status < 0)
+      cudaGetLastError();
+      e->last_graph_status = -1;
+      return enqueue_sample(e, a, s);
+    }
+    if (e->graphs.size() >= kMaxSampleGraphs) {
+      size_t oldest = 0;
+      for (size_t i = 1; i < e->graphs.size(); ++i)
+        if (e->graphs[i].stamp < e->graphs[oldest].stamp) oldest = i;
+      drop_graph(e, oldest);
+    }
+    e->graphs.push_back({key, exec, launches, 0});
+    hit = e->graphs.size() - 1;
+    e->last_graph_status = 1;
+  } else {
+    e->last_graph_status = 2;
+  }
+  gecco_engine::SampleGraph& g = e->graphs[hit];
+  g.stamp = ++e->graph_clock;
+  cudaError_t ce = cudaEventRecord(e->ev_fork, s);
+  if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->gstream, e->ev_fork, 0);
+  if (ce == cudaSuccess) ce = cudaGraphLaunch(g.exec, e->gstream);
+  if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_join, e->gstream);
+  if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, e->ev_join, 0);
+  if (ce != cudaSuccess) return fail_cuda(ce, "gecco_sample: graph launch");
+  g_launches += g.launches;
+  return GECCO_OK;
+}
+
+extern "C" int gecco_graph_status(const gecco_engine* e) { return e ? e->last_graph_status : 0; }
 
 // ------------------------------------------------------------------------------------------------ profiling
 extern "C" int gecco_profile_start(void) {

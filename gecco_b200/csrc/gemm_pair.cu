@@ -11,6 +11,7 @@
 //   warp 3 : residual loader
 //   warps 4-11 : epilogue (epilogue.cuh), each CTA on its own 128 rows
 #include "common.cuh"
+#include "debug_api.h"
 #include "epilogue.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"

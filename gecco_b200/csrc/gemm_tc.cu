@@ -393,6 +393,10 @@ extern "C" int gecco_set_option(const char* name, int value) {
     gecco::g_epi_skip = value;
     return GECCO_OK;
   }
+  if (name != nullptr && strcmp(name, "graphs") == 0) {
+    gecco::set_graphs_option(value);
+    return GECCO_OK;
+  }
   gecco::set_error("gecco_set_option: unknown option '%s'", name ? name : "(null)");
   return GECCO_ERR_INVALID;
 }

@@ -19,6 +19,7 @@ int make_residual_tmap(const float* res, long long ldr, int m, int n_out, const 
 int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t s, int* handled);
 
 int launch_gemm(const gecco_gemm_args& a, cudaStream_t s);
+void set_graphs_option(int value);  // engine.cu: gecco_set_option("graphs", v)
 // Fused MLP (mlp_fused.cu): GEMM -> Gaussian activation -> GEMM -> + residual with the hidden tensor on chip.
 bool mlp_fused_supported(const gecco_mlp_args& a);
 int launch_mlp_fused(const gecco_mlp_args& a, cudaStream_t s);

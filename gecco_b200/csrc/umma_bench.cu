@@ -7,6 +7,7 @@
 //   mode 3: A from TMEM, B MN-major
 // Not part of the product path.
 #include "common.cuh"
+#include "debug_api.h"
 #include "ptx.cuh"
 
 namespace gecco {

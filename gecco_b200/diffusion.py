@@ -67,8 +67,9 @@ class LogUniformSchedule(nn.Module):
     def forward(self, data: Tensor) -> Tensor:
         n = data.shape[0]
         u = torch.rand(n, device=data.device)
-        if self.low_discrepancy:
-            u = (u + torch.arange(n, device=data.device)) / n
+        if self.low_discrepancy:  # one stratum per example (diffusion.py:105-108), same operation order as the reference
+            div = 1 / n
+            u = div * u + div * torch.arange(n, device=data.device)
         sigma = (u * (self.log_sigma_max - self.log_sigma_min) + self.log_sigma_min).exp()
         return sigma.reshape(-1, *ones(data.ndim - 1))
 
@@ -187,16 +188,20 @@ class Diffusion(_Base):
         post_context = self.conditioner(context)
         ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])
         gammas = self._gammas(ts, num_steps, kw["S_churn"], kw["S_min"], kw["S_max"])
-        # one draw per step, even where gamma is 0 (diffusion.py:324)
-        noise = torch.empty((num_steps, *latents.shape), device=device, dtype=dtype)
+        net, sigma_data = self._network()
+        eng = engine_for(net, sigma_data)
+        # one draw per step, even where gamma is 0 (diffusion.py:324), straight into the engine's persistent noise buffer
+        if dtype == torch.float32 and len(latents.shape) == 3:
+            _, noise = eng.sample_buffers(latents.shape[0], latents.shape[1], num_steps, device)
+        else:
+            noise = torch.empty((num_steps, *latents.shape), device=device, dtype=dtype)
         for i in range(num_steps):
             if rng.device == device:
-                noise[i].normal_(generator=rng)  # == torch.randn(shape, generator=rng) written in place
+                noise[i].normal_(generator=rng)  # == torch.randn(shape, generator=rng) written in place (tests/test_noise_gpu.py)
             else:
                 noise[i].copy_(self._randn(latents.shape, rng, device, dtype))
-        net, sigma_data = self._network()
-        x = engine_for(net, sigma_data).sample(latents, noise, ts.tolist(), gammas, kw["S_noise"], post_context=post_context,
-                                               K=None if context is None else context.K)
+        x = eng.sample(latents, noise, ts.tolist(), gammas, kw["S_noise"], post_context=post_context,
+                       K=None if context is None else context.K)
         return self.reparam.diffusion_to_data(x, context)
 
     def _network(self):

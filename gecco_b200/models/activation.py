@@ -2,7 +2,7 @@
 
 g(x) = exp(-x^2 / (2 alpha^2)), optionally normalised to (g - 0.7) / 0.28, with one learnable scalar alpha.
 On the hot path it is applied inside the epilogue of the tcgen05 GEMM that produces its input
-(csrc/gemm_tc.cu, `act`); the module itself only owns `alpha`.
+(csrc/epilogue.cuh, `act`); called on its own, `forward` runs the `gecco_gaussian_activation` kernel.
 """
 import torch
 import torch.nn as nn
@@ -14,7 +14,8 @@ class GaussianActivation(nn.Module):
         self.alpha = nn.Parameter(torch.tensor(1.0))
         self.normalized = normalized
 
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError(
-            "gecco_b200: GaussianActivation is fused into the preceding projection; call the enclosing "
-            "MLP / Diffusion module instead")
+        from .. import ops
+
+        return ops.gaussian_activation(x, float(self.alpha), self.normalized)

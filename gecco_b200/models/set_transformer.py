@@ -1,15 +1,18 @@
 """Inducer-point SetTransformer: parameter containers with the reference's module tree
 (gecco_torch/models/set_transformer.py:14-216), so `state_dict()` keys and random initialisation match.
 
-The computation does not run module by module: `gecco_b200.engine.Engine` walks this tree once, packs the
-weights and runs the whole stack in the CUDA engine (csrc/engine.cu).  `SetTransformer.forward` is routed
-through the same engine (features in, features out).
+Inside a denoiser (`LinearLift` / `RayNetwork` / `EDMPrecond` / `Diffusion`) the computation does not run module by
+module: `gecco_b200.engine.Engine` walks this tree once, packs the weights and runs the whole stack fused in the CUDA
+engine (csrc/engine.cu).  Every module here ALSO has the reference's stand-alone `forward` (same arguments and return
+conventions), executed with the same C-ABI kernels through `models/_native.py`: tcgen05 GEMMs with fused bias /
+activation / residual epilogues, the two attention cores and the AdaGN kernels.  No torch math, no CPU path.
 """
 from __future__ import annotations
 
 import torch
 from torch import Tensor, nn
 
+from . import _native
 from .mlp import MLP
 from .normalization import AdaGN
 
@@ -27,6 +30,11 @@ class AttentionPool(nn.Module):
         self.kv_proj = nn.Linear(feature_dim, 2 * feature_dim, bias=False)
         self.out_proj = nn.Linear(feature_dim, feature_dim, bias=False)
 
+    @torch.no_grad()
+    def forward(self, kv: Tensor) -> Tensor:
+        """[B, N, C] -> [B, num_inducers, C] (set_transformer.py:47-65)."""
+        return _native.attention_pool_forward(self, kv)
+
 
 class Broadcast(nn.Module):
     """pool -> AdaGN -> MLP -> AdaGN on the inducers, then inducers -> points attention (set_transformer.py:68-117).
@@ -40,6 +48,20 @@ class Broadcast(nn.Module):
         self.mlp = MLP(feature_dim, feature_dim, mlp_blowup * feature_dim, activation=activation)
         self.norm_2 = AdaGN(feature_dim, t_embed_dim)
         self.unpool = nn.MultiheadAttention(feature_dim, num_heads, batch_first=True)
+
+    @torch.no_grad()
+    def forward(self, x: Tensor, t_embed: Tensor, return_h: bool = False, h: Tensor | None = None):
+        """(attn, h | None) like the reference (set_transformer.py:92-117); a given `h` skips the inducer side."""
+        return self._forward(x, t_embed, return_h, h, None)
+
+    def _forward(self, x, t_embed, return_h, h, residual):
+        if h is None:
+            h = self.pool(x)
+            h = self.norm_1(h, t_embed)
+            h = self.mlp(h)
+            h = self.norm_2(h, t_embed)
+        attn = _native.unpool_forward(self.unpool, x, h, residual)  # (+ residual in the out-projection epilogue)
+        return attn, (h if return_h else None)
 
 
 class BroadcastingLayer(nn.Module):
@@ -57,6 +79,16 @@ class BroadcastingLayer(nn.Module):
             self.broadcast.unpool.out_proj.weight.mul_(0.1)
             self.mlp[-1].weight.mul_(0.1)
 
+    @torch.no_grad()
+    def forward(self, x: Tensor, t_embed: Tensor, return_h: bool = False, h: Tensor | None = None):
+        """x += Broadcast(AdaGN(x)); x += MLP(AdaGN(x)) (set_transformer.py:155-168); both residual adds run in the
+        epilogue of the projection that produces the branch."""
+        y = self.broadcast_norm(x, t_embed)
+        x, h = self.broadcast._forward(y, t_embed, return_h, h, x)
+        y = self.mlp_norm(x, t_embed)
+        x = _native.mlp_forward(self.mlp, y, residual=x)
+        return x, h
+
 
 class SetTransformer(nn.Module):
     def __init__(self, n_layers: int, feature_dim: int, num_inducers: int, t_embed_dim: int, **kwargs):
@@ -66,7 +98,13 @@ class SetTransformer(nn.Module):
              for _ in range(n_layers)])
         self.feature_dim = feature_dim
 
+    @torch.no_grad()
     def forward(self, features: Tensor, t_embed: Tensor, return_h: bool = False, hs: list | None = None):
-        raise NotImplementedError(
-            "gecco_b200: the SetTransformer stack runs inside the denoiser engine; call it through LinearLift / "
-            "RayNetwork / EDMPrecond / Diffusion")
+        """(features, [h per layer] | None), consuming cached inducer states `hs` when given (set_transformer.py:198-216)."""
+        if hs is None:
+            hs = [None] * len(self.layers)
+        stored_h = []
+        for layer, h in zip(self.layers, hs):
+            features, h = layer(features, t_embed, return_h=return_h, h=h)
+            stored_h.append(h)
+        return (features, stored_h) if return_h else (features, None)

@@ -146,6 +146,16 @@ def mlp(a: Tensor, w1: Tensor, b1: Tensor, act_alpha: float, w2: Tensor, b2: Ten
     return out_f32, out_bf16
 
 
+def gaussian_activation(x: Tensor, alpha: float, normalized: bool = True) -> Tensor:
+    """GaussianActivation.forward as a stand-alone kernel (gecco_gaussian_activation)."""
+    lib = _lib_for(x)
+    xf = x.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(xf)
+    _abi.check(lib.gecco_gaussian_activation(_ptr(xf), _ptr(out), C.c_int64(xf.numel()), C.c_float(float(alpha)),
+                                             C.c_int32(1 if normalized else 0), _stream(xf)))
+    return out.to(x.dtype)
+
+
 STAT_GS = 12  # channel granularity of the AdaGN statistics kept by the GEMM epilogue (C / 32 for C = 384)
 
 
@@ -285,12 +295,13 @@ def reparam(x: Tensor, kind: int, to_data: bool, mean=None, sigma=None, logit_sc
     return out
 
 
-def pack_features(f: Tensor) -> Tensor:
-    """fp32 NCHW feature map -> bf16 NHWC (the layout gecco_lookup gathers from)."""
+def pack_features(f: Tensor, out: Tensor | None = None) -> Tensor:
+    """fp32 NCHW feature map -> bf16 NHWC (the layout gecco_lookup gathers from); `out` reuses an existing buffer."""
     lib = _lib_for(f)
     f = f.to(torch.float32).contiguous()
     b, c, h, w = f.shape
-    out = torch.empty((b, h, w, c), device=f.device, dtype=torch.bfloat16)
+    if out is None or tuple(out.shape) != (b, h, w, c) or out.device != f.device or out.dtype != torch.bfloat16:
+        out = torch.empty((b, h, w, c), device=f.device, dtype=torch.bfloat16)
     _abi.check(lib.gecco_pack_features(_ptr(f), _ptr(out), b, c, h, w, _stream(f)))
     return out
 

@@ -38,14 +38,10 @@ const char* gecco_last_error(void);
 /* Checks that `device` is sm_100 and resolves the driver entry points. */
 int gecco_init(int device);
 
-/* Tuning / debugging switches.  "gemm_pairs" (default 1): use the CTA-pair (cta_group::2) GEMM where it applies. */
+/* Tuning switches.  "gemm_pairs" (default 1): use the CTA-pair (cta_group::2) GEMM where it applies;
+ * "graphs" (default 1, or GECCO_GRAPHS=0 in the environment): gecco_sample captures its launch sequence into a
+ * CUDA graph on the first call with a given argument set and replays it afterwards. */
 int gecco_set_option(const char* name, int value);
-/* Development aid: device buffer ([148][16] int64) receiving per-CTA cycle counters of the CTA-pair GEMM; NULL disables. */
-int gecco_set_debug_buffer(void* buf);
-/* Development aid (tools/umma_bench.py): cycles for `batch` back-to-back M128 x n x K16 bf16 tcgen05.mma on one SM.
- * mode 0: A, B from shared memory (K-major); 1: B MN-major; 2: A from TMEM, B K-major; 3: A from TMEM, B MN-major.
- * out: device buffer of two int64 (best, mean over reps - 1 repetitions). */
-int gecco_debug_umma_bench(int32_t mode, int32_t n, int32_t batch, int32_t reps, long long* out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Dense projection on the tcgen05 tensor cores.
@@ -156,6 +152,11 @@ typedef struct gecco_fold_adagn_args {
   float* bias_folded; int32_t bias_stride;
 } gecco_fold_adagn_args;
 int gecco_fold_adagn(const gecco_fold_adagn_args* args, void* stream);
+
+/* GaussianActivation.forward (models/activation.py:17-24) as a stand-alone op on n contiguous floats (16-byte aligned):
+ * y = exp(-x^2 / (2 alpha^2)), then (y - 0.7) / 0.28 when normalized != 0.  In the denoiser it is fused into the
+ * epilogue of the projection that produces x (gecco_gemm `act`). */
+int gecco_gaussian_activation(const float* x, float* y, int64_t n, float alpha, int32_t normalized, void* stream);
 
 /* LinearLift.lift (models/linear_lift.py:21,44) on the EDM-scaled input:
  *   x[b,n,:] = W (c_in(sigma_b) * xin[b,n,:]) + bias, c_in = 1/sqrt(sigma_data^2 + sigma^2)
@@ -379,6 +380,10 @@ typedef struct gecco_sample_args {
   void* workspace; int64_t workspace_bytes;
 } gecco_sample_args;
 int gecco_sample(gecco_engine* e, const gecco_sample_args* args, void* stream);
+/* How the last gecco_sample call on this handle ran: 0 eager (graphs off, profiling, or the caller's stream is itself
+ * being captured), 1 captured into a CUDA graph and launched, 2 replayed a cached graph, -1 capture failed and the
+ * call ran eagerly.  A graph is reused only when every argument (shapes, schedule, all pointers) is identical. */
+int gecco_graph_status(const gecco_engine* e);
 
 /* Per-kernel-class device timing of the engine (tracing aid; the reference has none).  Between
  * start and stop every engine launch on this thread is bracketed by CUDA events on its stream; stop synchronises

@@ -280,3 +280,17 @@ def upsample(cfg: OracleConfig, sd: dict, data: Tensor, n_new: int | None = None
             if u < num_substeps - 1 and i < n - 1:
                 x_next = x_next + (t_cur**2 - t_next**2).sqrt() * randn(x_next.shape)
     return diffusion_to_data(cfg, sd, x_next, K)
+
+
+# diffusion.py:87-143 — LogUniformSchedule (low-discrepancy) + EDMLoss on given draws u ~ U[0,1)^B, noise ~ N(0,1)
+def edm_loss(cfg: OracleConfig, sd: dict, examples: Tensor, u: Tensor, noise: Tensor, features=None, K=None,
+             sigma_min: float = 0.002, loss_scale: float = 100.0) -> Tensor:
+    ex_diff = data_to_diffusion(cfg, sd, examples, K)
+    n = examples.shape[0]
+    div = 1 / n
+    uu = div * u + div * torch.arange(n)  # :105-108
+    lo, hi = math.log(sigma_min), math.log(cfg.sigma_max)
+    sigma = (uu * (hi - lo) + lo).exp().reshape(-1, 1, 1)  # :110-113
+    weight = (sigma**2 + cfg.sigma_data**2) / ((sigma * cfg.sigma_data) ** 2)  # :138
+    D = denoise(cfg, sd, ex_diff + noise * sigma, sigma, features, K)
+    return (loss_scale * weight * (D - ex_diff) ** 2).mean()  # :141-142

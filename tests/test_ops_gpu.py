@@ -215,6 +215,42 @@ def test_lookup_staged_matches_global_gather(cuda, monkeypatch, sizes, N, slices
     assert torch.allclose(stats, ref_stats, rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("sizes,slices", [((34, 17, 8), None), ((34, 17, 8), "4"), ((64, 32, 16), None)])
+def test_lookup_bench_shape_vs_grid_sample(cuda, monkeypatch, sizes, slices):
+    """The production lookup at the BENCHMARKED shape (2048 points per cloud; 137^2 pyramid -> staged kernel with S = 2
+    channel slices, 256^2 pyramid -> the kernel the engine picks there) directly against torch's F.grid_sample on the
+    same bf16-rounded maps (ray.py:64-87), not against another kernel of this repo."""
+    from gecco_b200 import ops
+
+    B, N = 4, 2048
+    g = _gen(21)
+    dims = (96, 192, 384)
+    feats = [torch.randn(B, c, s, s, generator=g) for c, s in zip(dims, sizes)]
+    K = torch.tensor([[1.0859, 0, 0.4964], [0, 1.0859, 0.4964], [0, 0, 1]]).expand(B, 3, 3).contiguous()
+    xin = torch.randn(B, N, 3, generator=g) * 2
+    sigma = torch.tensor([0.002, 0.5, 4.0, 165.0])
+    mean, sig = [0.0, 0.0, 1.0], [0.15, 0.15, 0.15]
+    geo = xin / (1 + sigma**2).sqrt()[:, None, None]
+    uv = _proj(geo * torch.tensor(sig) + torch.tensor(mean), K.unsqueeze(1))
+    grid = (uv.unsqueeze(2) * 2 - 1).to(cuda)
+    ref = torch.cat([F.grid_sample(f.bfloat16().float().to(cuda), grid, align_corners=False)[..., 0].transpose(1, 2) for f in feats], -1)
+    levels = [ops.pack_features(f.to(cuda)) for f in feats]
+    if slices is not None:
+        monkeypatch.setenv("GECCO_LOOKUP_SLICES", slices)
+    stats = torch.zeros(B, 16, 2, dtype=torch.float64, device=cuda)
+    _, o16 = ops.lookup(xin.to(cuda), levels, K.to(cuda), reparam_kind=1, mean=mean, sigma_r=sig, sigma=sigma.to(cuda),
+                        rows_per_cloud=N, out_bf16=True, stats=stats)
+    torch.cuda.synchronize()
+    got = o16.view(B, N, -1).float()
+    err = (got - ref).abs()
+    # bf16 output rounding (2^-9 relative) plus the rare point within float rounding of a pixel boundary
+    tol = 1e-2 * ref.abs().clamp_min(1.0)
+    assert (err > tol).float().mean().item() < 1e-3 and err.max().item() < 0.1, (err.max().item(), (err > tol).float().mean().item())
+    v = ref.view(B, N, 16, 42).double()
+    assert torch.allclose(stats[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+    assert torch.allclose(stats[..., 1], (v * v).sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+
+
 @pytest.mark.parametrize("kind,dtype", [("gaussian", torch.float32), ("uvl", torch.float32), ("uvl", torch.float64)])
 def test_reparam_roundtrip(cuda, kind, dtype):
     from gecco_b200 import ops

@@ -85,3 +85,47 @@ def test_upsample_argument_check():
     g, r, cfg, sd = load("uncond.pt")
     with pytest.raises(ValueError):  # diffusion.py:398-401
         O.upsample(cfg, sd, torch.zeros(1, 8, 3))
+
+
+@pytest.mark.parametrize("name", ["bench_uncond", "bench_cond_gaussian"])
+def test_bench_shape_goldens(name):
+    """The oracle against the reference at the benchmarked shape (B = 4, N = 2048): denoiser output, inducer states and
+    the EDM loss value; the conditional case rebuilds the reference's ConvNeXtExtractor pyramid from its seed."""
+    g = torch.load(GOLD / (name + ".pt"), weights_only=False)
+    r = g["recipe"]
+    cfg = O.OracleConfig(kind=r["kind"], reparam=r["reparam"], sigma_max=r["sigma_max"])
+    sd = synth.full_state_dict(r["kind"], r["reparam"], r["mean"], r["sigma"], r["weight_seed"])
+    B, N = r["B"], r["N"]
+    feats = K = None
+    if r["kind"] == "cond":
+        import torchvision.models as tvm
+
+        torch.manual_seed(r["convnext_seed"])
+        net = tvm.convnext_tiny(weights=None).eval()
+        for m in net.modules():
+            if isinstance(m, tvm.convnext.CNBlock):
+                m.stochastic_depth = torch.nn.Identity()
+        x = torch.rand(B, 3, r["image"], r["image"], generator=synth.gen(r["image_seed"]))
+        feats = []
+        with torch.no_grad():
+            for i in range(0, 6, 2):  # (downsampling, processing) pairs, first three stages (models/feature_pyramid.py:44-52)
+                x = net.features[i + 1](net.features[i](x))
+                feats.append(x)
+        for f, sub in zip(feats, g["pyramid_sub"]):
+            assert rel(f[:, ::8, ::3, ::3], sub) < TOL
+        K = synth.camera(B, r["K"])
+    x = torch.randn(B, N, 3, generator=synth.gen(r["x_seed"])) * r["x_scale"]
+    with torch.no_grad():
+        D, hs = O.denoise(cfg, sd, x, r["noise_sigma"], feats, K, return_h=True)
+    assert rel(D, g["D"]) < 5e-5
+    for h, hg in zip(hs, g["hs_sub"]):
+        assert rel(h[:, ::8, ::8], hg) < 5e-5
+    # EDM loss (diffusion.py:118-143) on the reference's draws
+    ex = O.diffusion_to_data(cfg, sd, torch.randn(B, N, 3, generator=synth.gen(r["ex_seed"])), K)
+    torch.manual_seed(r["loss_seed"])
+    u = torch.rand(B)
+    noise = torch.randn_like(ex)
+    assert torch.equal(u, g["loss_u"])
+    with torch.no_grad():
+        loss = O.edm_loss(cfg, sd, ex, u, noise, feats, K)
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * abs(g["loss"].item())
