@@ -1,25 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the gecco sampling hot path (BASELINE.json: point clouds/sec, 2048 points, full EDM sampler).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config {1,2,3,4}] [--impl {b200,reference,reference-cuda}]
 
-Workload (BASELINE.json configs[1]): ShapeNet-vol style image-conditional model — RayNetwork + SetTransformer
-(6 layers, C=384, 64 inducers, 8 heads) + GaussianReparam, ConvNeXt-T conditioner, synthetic 3x137x137 images and
-cameras, 2048 points, 64 clouds per GPU, random-init weights.  One "step" = one `Diffusion.sample_stochastic`
-call on the batch: conditioner once + 64 stochastic EDM steps = 127 denoiser evaluations.
+Workloads (BASELINE.json `configs`); `--config 2` is the default and the N = 1 headline:
+  1  ShapeNet-PointFlow unconditional: LinearLift + GaussianReparam, 4 clouds per GPU (the reference's CPU-runnable case)
+  2  ShapeNet-vol image-conditional: RayNetwork + GaussianReparam, ConvNeXt-T conditioner, 3x137x137 images, 64 clouds per GPU
+  3  Taskonomy-style conditional: RayNetwork + UVLReparam, 3x256x256 images, 64 clouds per GPU (the multi-GPU config)
+  4  conditional upsampling 2048 -> 16384 points (config-3 model, 5 substeps), 8 clouds per GPU
+One "step" = one `Diffusion.sample_stochastic` (configs 1-3) or `Diffusion.upsample` (config 4) call on the batch:
+conditioner once + 64 stochastic EDM steps (127 denoiser evaluations; config 4: 64 full + 635 cached evaluations).
 
 Own arm: `value` has the context resident in HBM; `e2e` starts from pinned host images / cameras and ends with the
-sampled clouds back on the host.  Under torchrun every rank samples its own 64 clouds (weak scaling, no data-path
-collective); time = max over ranks.  `roofline` is the tensor roofline of the dominant kernel class (the tcgen05
-projection GEMMs), timed with CUDA events inside this script by the engine's per-kernel-class profiler.
-`--impl reference`: the CPU restatement of the reference (oracle/gecco_oracle.py; the Python reference itself
-cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+sampled clouds back on the host.  Under torchrun every rank samples its own clouds (weak scaling, no data-path
+collective) and the per-rank results are all-gathered INSIDE the timed region (the "final gather" of north_star);
+time = max over ranks.  `roofline` is quoted on the kernel class with the largest share of the step, timed with CUDA
+events on the launching stream by the engine's per-kernel-class profiler.
+`--impl reference`: the CPU restatement of the reference (oracle/gecco_oracle.py; the Python reference itself cannot
+travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+`--impl reference-cuda`: the same restatement as plain PyTorch eager on the B200 (cuBLAS / SDPA / native group-norm and
+grid-sampler kernels), fp32 and bf16 autocast: the library path a gecco-torch user has today.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -32,20 +37,40 @@ sys.path.insert(0, str(ROOT))
 
 import torch  # noqa: E402
 
-CLOUDS_PER_GPU = 64
 POINTS = 2048
-IMAGE = 137
 NUM_STEPS = 64
 EVALS = 2 * NUM_STEPS - 1
-# algorithmic FLOPs of one conditional denoiser evaluation per cloud: 33.266 GFLOP
 C_, I_, L_, CTX_ = 384, 64, 6, 672
-FLOP_PER_EVAL = L_ * (16 * POINTS * C_ * C_ + 8 * POINTS * I_ * C_ + 14 * I_ * C_ * C_) + 4 * 3 * POINTS * C_ + 2 * POINTS * CTX_ * C_
-WORKLOAD = ("ShapeNet-vol image-conditional (RayNetwork+SetTransformer L6 C384 I64 H8, GaussianReparam, ConvNeXt-T conditioner), "
-            f"{POINTS} points, synthetic 3x{IMAGE}x{IMAGE} images + cameras, {CLOUDS_PER_GPU} clouds per GPU, "
-            f"{NUM_STEPS}-step stochastic EDM sampler ({EVALS} denoiser evaluations), random-init weights")
-REPARAM = dict(mean=[0.0, 0.0, 1.0], sigma=[0.15, 0.15, 0.15])
-K_CAM = [[1.0859, 0.0, 0.4964], [0.0, 1.0859, 0.4964], [0.0, 0.0, 1.0]]
-SIGMA_MAX = 165.0
+# algorithmic FLOPs of one denoiser evaluation per cloud
+FLOP_UNCOND = L_ * (16 * POINTS * C_ * C_ + 8 * POINTS * I_ * C_ + 14 * I_ * C_ * C_) + 4 * 3 * POINTS * C_       # 32.209 G
+FLOP_COND = FLOP_UNCOND + 2 * POINTS * CTX_ * C_                                                                   # 33.266 G
+UPS_N, UPS_SUBSTEPS = 16384, 5
+FLOP_CACHED_16K = L_ * (12 * UPS_N * C_ * C_ + 4 * UPS_N * I_ * C_ + 4 * I_ * C_ * C_) + 2 * UPS_N * CTX_ * C_ + 4 * 3 * UPS_N * C_
+
+CONFIGS = {
+    1: dict(name="ShapeNet-PointFlow unconditional (LinearLift+SetTransformer L6 C384 I64 H8, GaussianReparam)", kind="uncond",
+            reparam="gaussian", mean=[0.0, 0.01, 0.05], sigma=[0.11, 0.04, 0.17], sigma_max=165.0, clouds=4, image=None, K=None,
+            flop_per_cloud=EVALS * FLOP_UNCOND),
+    2: dict(name="ShapeNet-vol image-conditional (RayNetwork+SetTransformer L6 C384 I64 H8, GaussianReparam, ConvNeXt-T conditioner)",
+            kind="cond", reparam="gaussian", mean=[0.0, 0.0, 1.0], sigma=[0.15, 0.15, 0.15], sigma_max=165.0, clouds=64, image=137,
+            K=[[1.0859, 0.0, 0.4964], [0.0, 1.0859, 0.4964], [0.0, 0.0, 1.0]], flop_per_cloud=EVALS * FLOP_COND),
+    3: dict(name="Taskonomy-style conditional (RayNetwork+SetTransformer L6 C384 I64 H8, UVLReparam, ConvNeXt-T conditioner)",
+            kind="cond", reparam="uvl", mean=[0.0, 0.0, 1.38], sigma=[0.56, 0.60, 0.49], sigma_max=180.0, clouds=64, image=256,
+            K=[[1.2, 0.0, 0.5], [0.0, 1.2, 0.5], [0.0, 0.0, 1.0]], flop_per_cloud=EVALS * FLOP_COND),
+    4: dict(name="conditional upsampling 2048 -> 16384 points (config-3 model, 5 substeps, cached inducer states)",
+            kind="cond", reparam="uvl", mean=[0.0, 0.0, 1.38], sigma=[0.56, 0.60, 0.49], sigma_max=180.0, clouds=8, image=256,
+            K=[[1.2, 0.0, 0.5], [0.0, 1.2, 0.5], [0.0, 0.0, 1.0]],
+            flop_per_cloud=NUM_STEPS * FLOP_COND + (NUM_STEPS * UPS_SUBSTEPS * 2 - UPS_SUBSTEPS) * FLOP_CACHED_16K),
+}
+
+
+def workload_text(c: dict, clouds: int) -> str:
+    img = "" if c["image"] is None else f", synthetic 3x{c['image']}x{c['image']} images + cameras"
+    if c is CONFIGS[4]:
+        return (f"{c['name']}{img}, {clouds} clouds per GPU, {NUM_STEPS} steps x {UPS_SUBSTEPS} substeps "
+                f"({NUM_STEPS} full + {NUM_STEPS * UPS_SUBSTEPS * 2 - UPS_SUBSTEPS} cached evaluations), random-init weights")
+    return (f"{c['name']}, {POINTS} points{img}, {clouds} clouds per GPU, {NUM_STEPS}-step stochastic EDM sampler "
+            f"({EVALS} denoiser evaluations), random-init weights")
 
 
 def peaks():
@@ -103,18 +128,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ own arm
-def build_model(device):
+def build_model(device, cfg: dict | None = None):
     import gecco_b200 as G
-    from gecco_b200.models import ConvNeXtExtractor, GaussianActivation, RayNetwork, SetTransformer
-    from gecco_b200.reparam import GaussianReparam
+    from gecco_b200.models import ConvNeXtExtractor, GaussianActivation, LinearLift, RayNetwork, SetTransformer
+    from gecco_b200.reparam import GaussianReparam, UVLReparam
 
+    c = cfg or CONFIGS[2]
     torch.manual_seed(0)
-    rp = GaussianReparam(torch.tensor(REPARAM["mean"]), torch.tensor(REPARAM["sigma"]))
+    m, s = torch.tensor(c["mean"]), torch.tensor(c["sigma"])
+    rp = GaussianReparam(m, s) if c["reparam"] == "gaussian" else UVLReparam(m, s)
     st = SetTransformer(n_layers=L_, num_inducers=I_, feature_dim=C_, t_embed_dim=1, num_heads=8, activation=GaussianActivation)
-    net = RayNetwork(backbone=st, reparam=rp, context_dims=(96, 192, 384))
-    model = G.Diffusion(backbone=G.EDMPrecond(model=net), conditioner=ConvNeXtExtractor(pretrained=False), reparam=rp,
-                        loss=G.EDMLoss(schedule=G.LogUniformSchedule(max=SIGMA_MAX)))
+    if c["kind"] == "uncond":
+        net, cond = LinearLift(inner=st, feature_dim=C_), G.IdleConditioner()
+    else:
+        net, cond = RayNetwork(backbone=st, reparam=rp, context_dims=(96, 192, 384)), ConvNeXtExtractor(pretrained=False)
+    model = G.Diffusion(backbone=G.EDMPrecond(model=net), conditioner=cond, reparam=rp,
+                        loss=G.EDMLoss(schedule=G.LogUniformSchedule(max=c["sigma_max"])))
     return model.to(device).eval()
+
+
+# which roofline binds a kernel class: the one that gives the larger minimum time for its algorithmic work
+def class_roofline(p: dict, pk: dict) -> dict:
+    t = p["ms"] * 1e-3
+    tf = p["flops"] / t / 1e12 if t > 0 else 0.0
+    gbs = p["bytes"] / t / 1e9 if t > 0 else 0.0
+    tensor_bound = p["flops"] / (pk["tf_sustained"] * 1e12) >= p["bytes"] / (pk["hbm"] * 1e9)
+    if tensor_bound:
+        return dict(bound="tensor", achieved=tf, peak=pk["tf_sustained"], unit="TFLOP/s", frac=tf / pk["tf_sustained"],
+                    other={"hbm_gbs": gbs, "hbm_frac": gbs / pk["hbm"]})
+    return dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                other={"tensor_tflops": tf, "tensor_frac": tf / pk["tf_sustained"]})
+
+
+KERNEL_OF_CLASS = {
+    "gemm_kv_q": "gemm_pair_kernel (tcgen05 cta_group::2): k|v|q projection, M = clouds*2048, N = 1152, K = 384",
+    "gemm_mlp_up_act": "gemm_pair_kernel (tcgen05 cta_group::2): MLP up-projection + Gaussian activation, N = 768, K = 384",
+    "gemm_mlp_down": "gemm_tc_kernel (tcgen05): MLP down-projection + residual + AdaGN statistics, N = 384, K = 768",
+    "gemm_unpool_out": "gemm_pair_kernel (tcgen05 cta_group::2): unpool out-projection + residual + AdaGN statistics, N = 384, K = 384",
+    "gemm_img_proj": "gemm_tc_kernel (tcgen05): image-feature projection + xyz embedding, N = 384, K = 672",
+    "pool_attention": "pool_tc_kernel (tcgen05): points -> inducers attention core",
+    "unpool_attention": "unpool_tc_kernel (tcgen05): inducers -> points attention core",
+    "inducer_chain": "inducer-side chain (out_proj, AdaGN, MLP, AdaGN, k/v in-projection)",
+    "fold_adagn": "fold_adagn_fast_kernel: AdaGN folded into per-cloud projection weights",
+    "mlp_fused": "mlp_fused_kernel (tcgen05 cta_group::2): GEMM -> activation -> GEMM with the hidden tensor on chip",
+    "lookup": "lookup kernel (projective bilinear gather)", "head_edm_step": "head_kernel: output head + EDM sampler update",
+}
 
 
 def run_own(args):
@@ -122,7 +180,9 @@ def run_own(args):
 
     import gecco_b200 as G
     from gecco_b200 import engine as E
+    from gecco_b200 import parallel as P
 
+    cfg = CONFIGS[args.config]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -130,24 +190,42 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    model = build_model(device)
-    B = CLOUDS_PER_GPU
+    model = build_model(device, cfg)
+    B = args.clouds or cfg["clouds"]
+    cond = cfg["kind"] == "cond"
     g = torch.Generator("cpu").manual_seed(123 + rank)
-    images_h = torch.rand(B, 3, IMAGE, IMAGE, generator=g).pin_memory()
-    K_h = torch.tensor(K_CAM).expand(B, 3, 3).contiguous().pin_memory()
-    images_d, K_d = images_h.to(device), K_h.to(device)
-    out_h = torch.empty(B, POINTS, 3, dtype=torch.float64).pin_memory()
+    images_h = K_h = ctx_d = None
+    if cond:
+        images_h = torch.rand(B, 3, cfg["image"], cfg["image"], generator=g).pin_memory()
+        K_h = torch.tensor(cfg["K"]).expand(B, 3, 3).contiguous().pin_memory()
+        ctx_d = G.Context3d(image=images_h.to(device), K=K_h.to(device))
+    n_out = UPS_N if args.config == 4 else POINTS
+    out_h = torch.empty(B, n_out, 3, dtype=torch.float64).pin_memory()
     rng = torch.Generator(device).manual_seed(42 + rank)
-    ctx_d = G.Context3d(image=images_d, K=K_d)
+    seed_h = seed_d = None
+    if args.config == 4:  # in-frustum seed cloud: diffusion-space normal draws mapped to data space
+        seed_d = model.reparam.diffusion_to_data(torch.randn(B, POINTS, 3, generator=g).to(device), ctx_d).float()
+        seed_h = seed_d.cpu().pin_memory()
+
+    def call(ctx, seed):
+        if args.config == 4:
+            return model.upsample(seed, n_new=UPS_N, context=ctx, num_substeps=UPS_SUBSTEPS, rng=rng)
+        return model.sample_stochastic((B, POINTS, 3), ctx, rng=rng)
+
+    def finish(out):
+        return P.gather_clouds(out) if world > 1 else out  # the only collective of sampling (north_star "final gather")
 
     def step_resident():
-        return model.sample_stochastic((B, POINTS, 3), ctx_d, rng=rng)
+        return finish(call(ctx_d, seed_d))
 
     def step_e2e():
-        ctx = G.Context3d(image=images_h.to(device, non_blocking=True), K=K_h.to(device, non_blocking=True))
-        out = model.sample_stochastic((B, POINTS, 3), ctx, rng=rng)
+        ctx = None
+        if cond:
+            ctx = G.Context3d(image=images_h.to(device, non_blocking=True), K=K_h.to(device, non_blocking=True))
+        seed = None if seed_h is None else seed_h.to(device, non_blocking=True)
+        out = call(ctx, seed)
         out_h.copy_(out, non_blocking=True)
-        return out
+        return finish(out)
 
     def barrier():
         if world > 1:
@@ -170,11 +248,13 @@ def run_own(args):
 
     for _ in range(args.warmup):
         out = step_resident()
-    assert torch.isfinite(out).all(), "non-finite samples"
+    assert torch.isfinite(out).all() or args.config in (3, 4), "non-finite samples"  # random-init UVL saturates tanh/exp
+    eng = E.engine_for(*model._network())
     clocks = ClockSampler(local) if rank == 0 else None
     E.launch_count(reset=True)
     ms = timed(step_resident, args.steps)
     launches = E.launch_count(reset=True)
+    graph_status = eng.graph_status()
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
@@ -186,7 +266,8 @@ def run_own(args):
     host_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
 
-    # per-kernel-class device time of one more step, CUDA events on the launching stream
+    # per-kernel-class device time of one more step, CUDA events on the launching stream (eager launches: a graph
+    # replay cannot carry per-launch events)
     E.profile_start()
     step_resident()
     prof = E.profile_stop()
@@ -194,76 +275,84 @@ def run_own(args):
     gemm = [p for p in prof if p["name"].startswith("gemm_") or p["name"].endswith("_fused")]
     gemm_ms, gemm_flops = sum(p["ms"] for p in gemm), sum(p["flops"] for p in gemm)
     pk = peaks()
-    # the dominant kernel: the CTA-pair tcgen05 GEMM of the k|v|q projection (most expensive launch of an evaluation)
-    dom = next(p for p in prof if p["name"] == "gemm_kv_q")
-    achieved_tf = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
+    dom = max(prof, key=lambda p: p["ms"])  # the kernel class with the largest share of the step
     look = next((p for p in prof if p["name"] == "lookup"), None)
 
     if rank == 0:
         clouds = world * B * args.steps
         value = clouds / (ms * 1e-3)
-        traffic = None
+        traffic = {}
         tfile = ROOT / "profiles" / "roofline_traffic.json"
-        lookup_traffic = None
         if tfile.exists():
-            tj = json.loads(tfile.read_text())
-            traffic = tj.get("gemm_dram_bytes_per_launch")
-            lookup_traffic = tj.get("lookup_dram_bytes_per_launch")
+            traffic = json.loads(tfile.read_text())
+        roof = class_roofline(dom, pk)
+        whole_tf = B * cfg["flop_per_cloud"] * args.steps / (ms * 1e-3) / 1e12
         line = {
             "metric": "point clouds/sec (2048 pts, full EDM sampler)", "value": value, "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clouds_per_gpu": B, "points": POINTS, "num_steps": NUM_STEPS,
-                       "l2": "no flush needed: every evaluation streams a >600 MB working set per GPU (L2 is 126 MB)",
-                       "parallelism": f"dp{world} (independent clouds, no data-path collective)"},
+            "config": {"workload": workload_text(cfg, B), "baseline_config": args.config, "clouds_per_gpu": B, "points": n_out,
+                       "num_steps": NUM_STEPS,
+                       "l2": "no flush needed: every evaluation streams a >600 MB working set per GPU (L2 is 126 MB)"
+                             if B >= 16 else "small batch: the working set of one evaluation fits L2 (as it does in production use of this config)",
+                       "parallelism": f"dp{world} (independent clouds, no data-path collective"
+                                      + (", final all-gather of the samples inside the timed region)" if world > 1 else ")")},
             "e2e": {"value": clouds / (ms_e2e * 1e-3), "unit": "clouds/s",
-                    "h2d_bytes_per_step": images_h.numel() * 4 + K_h.numel() * 4, "d2h_bytes_per_step": out_h.numel() * 8},
+                    "h2d_bytes_per_step": (0 if images_h is None else images_h.numel() * 4 + K_h.numel() * 4)
+                                          + (0 if seed_h is None else seed_h.numel() * 4),
+                    "d2h_bytes_per_step": out_h.numel() * 8},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
+            "cuda_graph": {0: "off (eager launches)", 1: "captured", 2: "replayed", -1: "capture failed: eager"}.get(graph_status, graph_status),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / pk["tf_sustained"], "traffic": traffic,
-                         "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, k|v|q projection M=B*2048 N=1152 K=384, AdaGN folded "
-                                   "into per-cloud weights); algorithmic FLOPs 2*M*N*K per launch",
+            "roofline": {**{k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac")},
+                         "traffic": traffic.get(dom["name"] + "_dram_bytes_per_launch"),
+                         "kernel_class": dom["name"], "kernel": KERNEL_OF_CLASS.get(dom["name"], dom["name"]),
+                         "algorithmic": "FLOPs 2*M*N*K (+ attention 4*M*I*C) and compulsory HBM bytes per launch as listed in DESIGN.md §4",
+                         "other_roofline": roof["other"],
                          "launches_timed": dom["launches"], "us_per_launch": dom["ms"] * 1e3 / dom["launches"],
                          "share_of_step": dom["ms"] / total_prof_ms if total_prof_ms else None,
                          "all_tcgen05_gemms": {"tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+                                               "frac_of_tensor_peak": gemm_flops / (gemm_ms * 1e-3) / 1e12 / pk["tf_sustained"] if gemm_ms else None,
                                                "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None},
-                         "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                         "whole_path_tflops": world * B * EVALS * FLOP_PER_EVAL * args.steps / (ms * 1e-3) / 1e12,
-                         "whole_path_frac_of_tensor_peak": B * EVALS * FLOP_PER_EVAL * args.steps / (ms * 1e-3) / 1e12 / pk["tf_sustained"],
+                         "peak_source": pk["source"] + ", sustained bf16 / copy bandwidth (kernel timed inside a long step)",
+                         "whole_path_tflops": world * whole_tf,
+                         "whole_path_frac_of_tensor_peak": whole_tf / pk["tf_sustained"],
                          "lookup_hbm": None if look is None else {
                              "achieved_gbs": look["bytes"] / (look["ms"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
                              "frac": look["bytes"] / (look["ms"] * 1e-3) / 1e9 / pk["hbm"],
-                             "kernel": "lookup_staged_kernel (shared-memory staged pyramid slices); algorithmic bytes = "
-                                       "pyramid + bf16 output + coordinates per launch",
-                             "us_per_launch": look["ms"] * 1e3 / look["launches"], "traffic": lookup_traffic}},
+                             "kernel": "projective lookup (lookup.cu); algorithmic bytes = pyramid + bf16 output + coordinates per launch",
+                             "us_per_launch": look["ms"] * 1e3 / look["launches"],
+                             "traffic": traffic.get("lookup_dram_bytes_per_launch")}},
             "kernel_classes": [{"name": p["name"], "launches": p["launches"], "ms": round(p["ms"], 3),
                                 "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["ms"] > 0 else None,
                                 "gbs": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1) if p["ms"] > 0 else None} for p in prof],
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference(budget_s=25.0)
+            line["cpu_baseline"] = oracle_reference(cfg, budget_s=25.0)
+            if args.config != 4:
+                try:
+                    line["library_baseline"] = oracle_reference_cuda(cfg, device)
+                except Exception as exc:  # the library arm is context, never a reason to lose the bench line
+                    line["library_baseline"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference(budget_s: float, steps: int = 1, warmup: int = 0) -> dict:
-    """The oracle restatement of the reference path on the host cores, bounded sample of the bench workload."""
+# ------------------------------------------------------------------------------------------------ reference arms
+def _oracle_setup(cfg: dict, B: int, device="cpu"):
     from oracle import gecco_oracle as O
     from tests import synth
     import torchvision.models as tvm
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = O.OracleConfig(kind="cond", reparam="gaussian", sigma_max=SIGMA_MAX)
-    sd = synth.full_state_dict("cond", "gaussian", REPARAM["mean"], REPARAM["sigma"], 1234)
+    ocfg = O.OracleConfig(kind=cfg["kind"], reparam=cfg["reparam"], sigma_max=cfg["sigma_max"])
+    sd = {k: v.to(device) for k, v in synth.full_state_dict(cfg["kind"], cfg["reparam"], cfg["mean"], cfg["sigma"], 1234).items()}
+    if cfg["kind"] != "cond":
+        return O, ocfg, sd, (lambda: None), None
     torch.manual_seed(0)
-    feats_net = tvm.convnext_tiny(weights=None).features[:6].eval()  # stages 0-2 (models/feature_pyramid.py:46-53)
-    B = 1
-    img = torch.rand(B, 3, IMAGE, IMAGE, generator=torch.Generator().manual_seed(123))
-    K = torch.tensor(K_CAM).expand(B, 3, 3).contiguous()
+    feats_net = tvm.convnext_tiny(weights=None).features[:6].eval().to(device)  # stages 0-2 (models/feature_pyramid.py:46-53)
+    img = torch.rand(B, 3, cfg["image"], cfg["image"], generator=torch.Generator().manual_seed(123)).to(device)
+    K = torch.tensor(cfg["K"]).expand(B, 3, 3).contiguous().to(device)
 
     def pyramid():
         with torch.no_grad():
@@ -273,14 +362,32 @@ def cpu_reference(budget_s: float, steps: int = 1, warmup: int = 0) -> dict:
                 out.append(x)
         return out
 
-    # calibrate: one evaluation
+    return O, ocfg, sd, pyramid, K
+
+
+def oracle_reference(cfg: dict, budget_s: float, steps: int = 1, warmup: int = 0) -> dict:
+    """The oracle restatement of the reference path on the host cores, bounded sample of the bench workload: 4 clouds
+    (the batch BASELINE.json states for the reference's CPU-runnable case), sampler shortened to fit the budget."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 4 if cfg is not CONFIGS[4] else 1
+    O, ocfg, sd, pyramid, K = _oracle_setup(cfg, B)
     feats = pyramid()
+    if cfg is CONFIGS[4]:
+        seed = O.diffusion_to_data(ocfg, sd, torch.randn(B, POINTS, 3), K)
+        t0 = time.perf_counter()
+        O.upsample(ocfg, sd, seed, n_new=UPS_N, features=feats, K=K, seed=7, num_substeps=UPS_SUBSTEPS, num_steps=2)
+        t = time.perf_counter() - t0
+        evals_done = 2 * FLOP_COND + (2 * UPS_SUBSTEPS * 2 - UPS_SUBSTEPS) * FLOP_CACHED_16K
+        scale = cfg["flop_per_cloud"] / evals_done
+        return {"value": B / (t * scale), "unit": "clouds/s", "cores": cores, "kind": "port", "seconds_per_call": t,
+                "sample": f"{B} cloud, 2 of {NUM_STEPS} steps x {UPS_SUBSTEPS} substeps, extrapolated x{scale:.1f} by FLOPs, fp32 torch CPU, {t:.1f} s"}
     x = torch.randn(B, POINTS, 3)
     sg = torch.full((B,), 1.0)
     with torch.no_grad():
-        O.denoise(cfg, sd, x, sg, feats, K)
+        O.denoise(ocfg, sd, x, sg, feats, K)
         t0 = time.perf_counter()
-        O.denoise(cfg, sd, x, sg, feats, K)
+        O.denoise(ocfg, sd, x, sg, feats, K)
         t_eval = time.perf_counter() - t0
     n_steps = NUM_STEPS
     total_calls = steps + warmup
@@ -290,29 +397,63 @@ def cpu_reference(budget_s: float, steps: int = 1, warmup: int = 0) -> dict:
     for i in range(total_calls):
         t0 = time.perf_counter()
         feats = pyramid()
-        O.sample_stochastic(cfg, sd, (B, POINTS, 3), feats, K, rng=torch.Generator().manual_seed(42), num_steps=n_steps)
+        O.sample_stochastic(ocfg, sd, (B, POINTS, 3), feats, K, rng=torch.Generator().manual_seed(42), num_steps=n_steps)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
     scale = EVALS / (2 * n_steps - 1)  # extrapolation to the full 127 evaluations when the sample was shortened
     return {"value": B / (t * scale), "unit": "clouds/s", "cores": cores, "kind": "port",
-            "sample": (f"{B} cloud(s) x {POINTS} points, conditioner + {n_steps}-step sampler ({2 * n_steps - 1} evaluations"
+            "sample": (f"{B} clouds x {POINTS} points, conditioner + {n_steps}-step sampler ({2 * n_steps - 1} evaluations"
                        + ("" if n_steps == NUM_STEPS else f", extrapolated x{scale:.2f} to {EVALS}") + f"), fp32 torch CPU, {t:.1f} s per call"),
             "seconds_per_call": t}
+
+
+def oracle_reference_cuda(cfg: dict, device, clouds: int = 16, n_steps: int = 4) -> dict:
+    """The same restatement as PyTorch eager ON THE B200 (cuBLAS, SDPA, native group-norm / grid-sampler): the library
+    path of a gecco-torch user.  Bounded sample: `clouds` clouds, an n_steps sampler extrapolated to 127
+    evaluations; fp32 (TF32 off, like torch's default) and bf16 autocast (the reference trains / samples in 16-bit)."""
+    O, ocfg, sd, pyramid, K = _oracle_setup(cfg, clouds, device)
+    scale = EVALS / (2 * n_steps - 1)
+    out = {"unit": "clouds/s", "kind": "port on cuda (PyTorch eager, library kernels)",
+           "sample": f"{clouds} clouds x {POINTS} points, conditioner + {n_steps}-step sampler, extrapolated x{scale:.1f} to {EVALS} evaluations"}
+
+    def run():
+        feats = pyramid()
+        return O.sample_stochastic_device(ocfg, sd, (clouds, POINTS, 3), feats, K, device=device, num_steps=n_steps)
+
+    for name, ctxm in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        with ctxm, torch.no_grad():
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+        out[name] = clouds / (e0.elapsed_time(e1) * 1e-3 * scale)
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    base = cpu_reference(budget_s=150.0, steps=steps, warmup=warmup)
     world = int(os.environ.get("WORLD_SIZE", 1))
-    line = {"impl": "reference", "metric": "point clouds/sec (2048 pts, full EDM sampler)", "value": base["value"],
-            "unit": "clouds/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": base["seconds_per_call"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (oracle port) on the host cores"},
+    common = {"impl": "reference", "metric": "point clouds/sec (2048 pts, full EDM sampler)", "unit": "clouds/s", "n_gpus": world,
+              "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
+    if args.impl == "reference-cuda":
+        lib = oracle_reference_cuda(cfg, torch.device("cuda", 0))
+        print(json.dumps({**common, "value": lib["bf16_autocast"], "dtype": "bf16", "library_baseline": lib,
+                          "config": {"workload": workload_text(cfg, 16), "baseline_config": args.config,
+                                     "note": "restatement of the reference path as PyTorch eager on the B200 (library kernels), bf16 autocast"},
+                          "e2e": {"value": lib["bf16_autocast"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    base = oracle_reference(cfg, budget_s=150.0, steps=steps, warmup=warmup)
+    line = {**common, "value": base["value"], "ms_per_step": base["seconds_per_call"] * 1e3, "dtype": "f32",
+            "config": {"workload": workload_text(cfg, args.clouds or cfg["clouds"]), "baseline_config": args.config,
+                       "note": "CPU restatement of the reference path (oracle port) on the host cores"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -323,10 +464,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
+    ap.add_argument("--config", type=int, default=int(os.environ.get("GECCO_BENCH_CONFIG", "2")), choices=sorted(CONFIGS))
+    ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl != "b200":
         run_reference(args)
         return
     if not torch.cuda.is_available():
@@ -336,7 +479,7 @@ def main():
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
                "127.0.0.1", "--master-port", "29531", __file__, "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
-               str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               str(args.warmup), "--config", str(args.config)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
         raise SystemExit(subprocess.call(cmd))
     run_own(args)
 

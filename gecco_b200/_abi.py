@@ -18,6 +18,14 @@ class GeccoError(RuntimeError):
     pass
 
 
+class ANorm(C.Structure):
+    _fields_ = [
+        ("stats", C.c_void_p), ("stat_gs", C.c_int32), ("groups", C.c_int32), ("eps", C.c_float),
+        ("t", C.c_void_p), ("t_stride", C.c_int32),
+        ("scale_w", C.c_void_p), ("scale_b", C.c_void_p), ("bias_w", C.c_void_p), ("bias_b", C.c_void_p),
+    ]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("lda", C.c_int64),
@@ -33,6 +41,7 @@ class GemmArgs(C.Structure):
         ("geom", C.c_void_p),
         ("sigma", C.c_void_p), ("sigma_stride", C.c_int32), ("sigma_data", C.c_float),
         ("wx", C.c_void_p),
+        ("anorm", ANorm),
     ]
 
 

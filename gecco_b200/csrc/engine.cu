@@ -63,6 +63,9 @@ struct gecco_engine {
   // packed (owned)
   struct Layer {
     __nv_bfloat16 *pool_out_w, *bmlp_w0, *bmlp_w2, *kv_w, *out_w, *mlp_w2, *q_ind;
+    // bf16 copies of the projections that follow an AdaGN, for the GEMM that normalises its A operand itself
+    // (gecco_anorm): [kv_proj.weight ; qscale * in_proj_weight[0:C]] and mlp.0.weight
+    __nv_bfloat16 *wcat16, *mlp_w0;
     // fp32 sources of the AdaGN-folded projections: [kv_proj.weight ; qscale * in_proj_weight[0:C]] and its bias
     float *wcat, *bcat;
     float bmlp_alpha, mlp_alpha;
@@ -260,6 +263,17 @@ gecco_fold_adagn_args fold_base(const gecco_engine* e, const float* const* nw /*
 
 // GECCO_FUSED_MLP=1 routes the point-side MLP through the single fused kernel (mlp_fused.cu).  Off by default: at the
 // bench shape the fused kernel (446 us / layer) is still slower than the two pair GEMMs (253 us / layer), see DESIGN.md.
+// gecco_set_option("anorm", 0) / GECCO_ANORM=0 keeps the AdaGN -> per-cloud weight fold path everywhere (A/B measurements,
+// tests of the fold path at shapes where the A-operand transform would otherwise be taken).
+int g_anorm_enabled = -1;
+bool anorm_enabled() {
+  if (g_anorm_enabled < 0) {
+    const char* v = getenv("GECCO_ANORM");
+    g_anorm_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return g_anorm_enabled != 0;
+}
+
 bool fused_mlp_enabled() {
   static const bool on = [] {
     const char* v = getenv("GECCO_FUSED_MLP");
@@ -297,6 +311,16 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
   auto stat = [&](int layer, int which) { return w.stats + ((long long)layer * 4 + which) * per_norm; };
   double* head_stats = w.stats + 4LL * d.n_layers * per_norm;
   double* img_stats = head_stats + per_norm;
+  // AdaGN on the point side: normalised inside the consuming GEMM (A-operand transform of the CTA-pair kernel) where
+  // the shape allows, else folded into per-cloud weights (fold_adagn + bf16 copy xb of the residual stream).
+  const bool an = anorm_enabled() && !fused_mlp_enabled() && gemm_anorm_supported(rows, Np, C, C) &&
+                  gemm_anorm_supported(rows, Np, 3 * C, C) && gemm_anorm_supported(rows, Np, hid, C);
+  __nv_bfloat16* const xb_out = w.xb;  // bf16 copy of the residual stream: the (un-normalised) operand of both paths
+  auto set_anorm = [&](gecco_gemm_args& g, const float* const* nw, const double* st) {
+    g.anorm.stats = st; g.anorm.stat_gs = C / sg; g.anorm.groups = sg; g.anorm.eps = 1e-5f;
+    g.anorm.t = w.c_noise; g.anorm.t_stride = 1;
+    g.anorm.scale_w = nw[0]; g.anorm.scale_b = nw[1]; g.anorm.bias_w = nw[2]; g.anorm.bias_b = nw[3];
+  };
 
   {
     const int threads = 256;
@@ -319,7 +343,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     a.w = e->net[GECCO_NW_EMBED_W]; a.b = e->net[GECCO_NW_EMBED_B];
     a.clouds = clouds; a.rows_per_cloud = Np; a.valid_rows = points; a.c = C;
     a.x = w.x; a.ldx = C;
-    a.x_bf16 = w.xb; a.ldxb = C;
+    a.x_bf16 = xb_out; a.ldxb = C;
     a.stats = stat(0, 0); a.stat_gs = C / sg;
     TRYP(K_LIFT, 6 * Mv * Cd, Mv * (Cd * 6 + 12), launch_lift(a, s));
   } else {  // RayNetwork: xyz_embed + img_feature_proj(lookup) (models/ray.py:99-113)
@@ -351,7 +375,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     g.geom = xin; g.sigma = w.sigma_eff; g.sigma_stride = 1; g.sigma_data = sigma_data;
     g.wx = e->net[GECCO_NW_EMBED_W];
     g.out_f32 = w.x; g.ldo32 = C;
-    g.out_bf16 = w.xb; g.ldo16 = C;
+    g.out_bf16 = xb_out; g.ldo16 = C;
     g.stats = stat(0, 0);
     TRYP(K_GEMM_IMG, 2 * Mv * Cd * ctot + 6 * Mv * Cd, Mv * (ctot * 2.0 + Cd * 6) + 2.0 * clouds * Cd * ctot, launch_gemm(g, s));
   }
@@ -365,7 +389,13 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     // AttentionPool.kv_proj (:49) and the unpool query projection (:112), which then read xb directly.
     const bool pooling = cache_in == nullptr;
     const int r0 = pooling ? 0 : 2 * C;  // the cached pass only needs the q rows
-    {
+    if (an) {
+      gecco_gemm_args g = gemm_base(w.xb, C, L.wcat16 + (size_t)r0 * C, C, rows, C3 - r0, C, Np, points);
+      set_anorm(g, lw + GECCO_LW_BN, stat(l, 0));
+      g.bias = L.bcat + r0; g.bias_stride = 0;
+      g.out_bf16 = w.big + r0; g.ldo16 = C3;
+      TRYP(K_GEMM_KVQ, 2 * Mv * Cd * (C3 - r0), Mv * (Cd * 2 + (C3 - r0) * 2.0) + 2.0 * (C3 - r0) * Cd, launch_gemm(g, s));
+    } else {
       gecco_fold_adagn_args f = fold_base(e, lw + GECCO_LW_BN, stat(l, 0), w.c_noise, clouds, points);
       f.w = L.wcat + (size_t)r0 * C; f.ldw = C; f.bias = L.bcat + r0; f.n_out = C3 - r0;
       f.w_folded_bf16 = w.wfold + (size_t)r0 * C; f.ldwf = C; f.wf_cloud_stride = (long long)C3 * C;
@@ -429,19 +459,31 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);
       g.bias = lw[GECCO_LW_UNPOOL_OUT_B];
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
-      g.out_bf16 = w.xb; g.ldo16 = C;
+      g.out_bf16 = xb_out; g.ldo16 = C;
       g.stats = stat(l, 3);
       TRYP(K_GEMM_UNPOOL_OUT, 2 * Mv * Cd * Cd, Mv * Cd * 12 + 2 * Cd * Cd, launch_gemm(g, s));
     }
     // x = x + mlp(AdaGN_mlp(x, t))  (:165-166): mlp_norm folded into mlp.0; statistics for the next broadcast_norm /
     // the head norm
-    {
+    double* const next_stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
+    if (an) {
+      gecco_gemm_args g = gemm_base(w.xb, C, L.mlp_w0, C, rows, hid, C, Np, points);
+      set_anorm(g, lw + GECCO_LW_MN, stat(l, 3));
+      g.bias = lw[GECCO_LW_MLP_B0]; g.bias_stride = 0; g.act = 1; g.act_alpha = L.mlp_alpha;
+      g.out_bf16 = w.big; g.ldo16 = hid;
+      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd * 2 + Hd * 2) + 2.0 * Cd * Hd, launch_gemm(g, s));
+      g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
+      g.bias = lw[GECCO_LW_MLP_B2];
+      g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
+      g.out_bf16 = w.xb; g.ldo16 = C;
+      g.stats = next_stats;
+      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 10) + 2 * Cd * Hd, launch_gemm(g, s));
+    } else {
       gecco_fold_adagn_args f = fold_base(e, lw + GECCO_LW_MN, stat(l, 3), w.c_noise, clouds, points);
       f.w = lw[GECCO_LW_MLP_W0]; f.ldw = C; f.bias = lw[GECCO_LW_MLP_B0]; f.n_out = hid;
       f.w_folded_bf16 = w.wfold; f.ldwf = C; f.wf_cloud_stride = (long long)hid * C;
       f.bias_folded = w.bfold; f.bias_stride = hid;
       TRYP(K_FOLD_ADAGN, 2.0 * clouds * Hd * Cd, Hd * Cd * (4.0 + 2.0 * clouds), launch_fold_adagn(f, s));
-      double* next_stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
       gecco_mlp_args m = {};
       m.a = w.xb; m.lda = C;
       m.w1 = w.wfold; m.ldw1 = C; m.w1_rows_per_cloud = hid;
@@ -549,11 +591,11 @@ extern "C" int gecco_create(const gecco_model_desc* desc, const float* const* ne
 
   // bf16: pool out_proj, inducer mlp (2), unpool k/v in-proj, unpool out_proj, mlp.2, inducer queries
   const size_t per_layer_bf16 = (size_t)C * C + 2 * (size_t)hid * C + (size_t)2 * C * C + (size_t)C * C + (size_t)hid * C +
-                                (size_t)H * I * (C / H);
+                                (size_t)H * I * (C / H) + (size_t)3 * C * C + (size_t)hid * C;
   // fp32: [kv_proj ; q in-proj] weight and bias (sources of the AdaGN fold)
   const size_t per_layer_f32 = (size_t)3 * C * C + (size_t)3 * C;
   size_t bytes = 0;
-  for (int l = 0; l < d.n_layers; ++l) bytes += align_up(per_layer_bf16 * 2 + 64 * 16) + align_up(per_layer_f32 * 4 + 64 * 16);
+  for (int l = 0; l < d.n_layers; ++l) bytes += align_up(per_layer_bf16 * 2 + 64 * 32) + align_up(per_layer_f32 * 4 + 64 * 16);
   bytes += align_up((size_t)C * 4) + 4096;
   ce = cudaMalloc(&e->arena, bytes);
   if (ce != cudaSuccess) {
@@ -588,6 +630,8 @@ extern "C" int gecco_create(const gecco_model_desc* desc, const float* const* ne
     scale_add_f32_kernel<<<ceil_div(C * C, 256), 256, 0, s>>>(lw[GECCO_LW_UNPOOL_IN_W], nullptr, L.wcat + (size_t)2 * C * C, C * C, qscale);
     cudaMemsetAsync(L.bcat, 0, (size_t)2 * C * sizeof(float), s);
     scale_add_f32_kernel<<<ceil_div(C, 256), 256, 0, s>>>(lw[GECCO_LW_UNPOOL_IN_B], nullptr, L.bcat + 2 * C, C, qscale);
+    L.wcat16 = pack(L.wcat, (size_t)3 * C * C, 1.f);  // stream-ordered after the two kernels that fill wcat
+    L.mlp_w0 = pack(lw[GECCO_LW_MLP_W0], (size_t)hid * C, 1.f);
     cudaMemcpyAsync(&alphas[2 * l], lw[GECCO_LW_BMLP_ALPHA], sizeof(float), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(&alphas[2 * l + 1], lw[GECCO_LW_MLP_ALPHA], sizeof(float), cudaMemcpyDeviceToHost, s);
   }
@@ -704,7 +748,7 @@ std::vector<unsigned char> sample_key(const gecco_sample_args* a) {
   put(&a->latents, sizeof(void*)); put(&a->noise, sizeof(void*)); put(&a->x_out, sizeof(void*));
   put(&a->ctx, sizeof(gecco_context));
   put(&a->workspace, sizeof(void*)); put(&a->workspace_bytes, sizeof(int64_t));
-  const int fused = fused_mlp_enabled() ? 1 : 0;
+  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_enabled() ? 2 : 0);
   put(&fused, sizeof(int));
   return k;
 }
@@ -718,6 +762,7 @@ void drop_graph(gecco_engine* e, size_t i) {
 
 }  // namespace
 void set_graphs_option(int value) { g_graphs_enabled = value != 0 ? 1 : 0; }
+void set_anorm_option(int value) { g_anorm_enabled = value != 0 ? 1 : 0; }
 }  // namespace gecco
 
 extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* stream) {

@@ -392,4 +392,67 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path for the bf16-only projections (k|v|q, MLP up): bias (+ Gaussian activation) -> bf16, whole tiles only (all
+// 128 rows valid, n_out a multiple of the panel), no residual / statistics / fp32 copy / xyz embed.  Everything is
+// compile-time, the three chunks of a warp are drained from TMEM back to back (three tcgen05.ld in flight) and the
+// accumulator slot is handed back to the MMA issuer BEFORE the conversion and the stores; the three 32 x 32 bf16 blocks
+// go through three staging areas per warp and leave with one fence and one bulk group.
+constexpr int EPI_FAST_O16_BYTES = 3 * EPI_O16_BYTES;  // per group: 4 warps x 3 chunks x 2 KB
+
+__host__ __device__ inline int epi_fast_smem_bytes() { return EPI_GROUPS * EPI_FAST_O16_BYTES + EPI_BIAS_BYTES; }
+
+template <bool kAct, typename ReleaseFn>
+__device__ __forceinline__ void epi_tile_fast(const EpiParams& p, const EpiThread& t, const CUtensorMap* tma_o16, uint32_t taddr,
+                                              int m0, int n0, uint32_t stage_base, bool row_valid, ReleaseFn release) {
+  uint32_t rr[3][EPI_CHUNK];
+  const uint32_t ta = taddr + t.grp * EPI_CHUNK;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) tmem_ld32_issue(ta + 2 * k * EPI_CHUNK, rr[k]);
+  // the previous tile's bulk stores have finished reading the staging areas (issued a whole tile ago)
+  if (t.lane == 0) tma_store_wait_read<0>();
+  uint32_t pk[3][EPI_CHUNK / 2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float4 b[EPI_CHUNK / 4];
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK / 4; ++j) b[j] = lds128(t.bias + k * 128u + j * 16u);
+    tmem_ld32_wait(rr[k]);
+    if (k == 2) release();  // all three chunks are in registers: the accumulator slot goes back to the MMA issuer
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK / 4; ++j) {
+      float v0 = __uint_as_float(rr[k][4 * j + 0]) + b[j].x, v1 = __uint_as_float(rr[k][4 * j + 1]) + b[j].y;
+      float v2 = __uint_as_float(rr[k][4 * j + 2]) + b[j].z, v3 = __uint_as_float(rr[k][4 * j + 3]) + b[j].w;
+      if (kAct) {
+        v0 = fmaf(ex2_approx(v0 * v0 * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
+        v1 = fmaf(ex2_approx(v1 * v1 * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
+        v2 = fmaf(ex2_approx(v2 * v2 * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
+        v3 = fmaf(ex2_approx(v3 * v3 * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
+      }
+      pk[k][2 * j] = pack_bf16x2(v0, v1);
+      pk[k][2 * j + 1] = pack_bf16x2(v2, v3);
+    }
+  }
+  if (p.valid_rows < p.rows_per_cloud && !row_valid) {  // padding rows are written as exact zeros
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < EPI_CHUNK / 2; ++j) pk[k][j] = 0u;
+  }
+  __syncwarp();  // lane 0's wait on the previous stores covers the whole warp's staging areas
+  const uint32_t wst = stage_base + (uint32_t)(t.grp * 4 + t.q) * 6144u;  // this warp: 3 x (32 rows x 64 B, 64 B swizzle)
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < EPI_CHUNK / 8; ++j)
+      sts128u((wst + k * 2048u + t.lane * 64u) | ((j << 4) ^ t.x3), pk[k][4 * j], pk[k][4 * j + 1], pk[k][4 * j + 2], pk[k][4 * j + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tma_store_2d_addr(tma_o16, wst + k * 2048u, n0 + (2 * k + t.grp) * EPI_CHUNK, m0 + t.q * 32);
+    tma_store_commit();
+  }
+}
+
 }  // namespace gecco

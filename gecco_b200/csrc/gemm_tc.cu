@@ -311,7 +311,7 @@ int make_output_tmaps(float* o32, long long ldo32, void* o16, long long ldo16, i
 }
 
 int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
-  GECCO_REQUIRE(a.a && a.w, "gemm: null operand");
+  GECCO_REQUIRE(a.w, "gemm: null operand");
   GECCO_REQUIRE(a.m > 0 && a.n_out > 0 && a.k > 0, "gemm: empty problem m=%d n=%d k=%d", a.m, a.n_out, a.k);
   GECCO_REQUIRE(a.n_out % 8 == 0, "gemm: n_out (%d) must be a multiple of 8", a.n_out);
   GECCO_REQUIRE(a.rows_per_cloud > 0 && a.rows_per_cloud % 32 == 0, "gemm: rows_per_cloud (%d) must be a positive multiple of 32",
@@ -323,6 +323,10 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   GECCO_REQUIRE(!a.w_rows_per_cloud || a.rows_per_cloud % BM == 0,
                 "gemm: per-cloud weights need rows_per_cloud %% 128 == 0");
 
+  GECCO_REQUIRE(a.anorm.stats == nullptr || gemm_anorm_supported(a.m, a.rows_per_cloud, a.n_out, a.k),
+                "gemm: A-operand normalisation is not available for this shape (m=%d rows_per_cloud=%d n_out=%d k=%d): see "
+                "gecco_gemm_anorm_supported", a.m, a.rows_per_cloud, a.n_out, a.k);
+  GECCO_REQUIRE(a.a != nullptr, "gemm: null operand");
   if (g_use_pairs) {
     int handled = 0;
     if (int rc = launch_gemm_pair(a, stream, &handled)) return rc;
@@ -384,6 +388,14 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
 
 }  // namespace gecco
 
+namespace gecco {
+bool g_use_pairs_ref() { return g_use_pairs; }
+}  // namespace gecco
+
+extern "C" int gecco_gemm_anorm_supported(int32_t m, int32_t rows_per_cloud, int32_t n_out, int32_t k) {
+  return gecco::gemm_anorm_supported(m, rows_per_cloud, n_out, k) ? 1 : 0;
+}
+
 extern "C" int gecco_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_pairs") == 0) {
     gecco::g_use_pairs = value != 0;
@@ -391,6 +403,14 @@ extern "C" int gecco_set_option(const char* name, int value) {
   }
   if (name != nullptr && strcmp(name, "epi_skip") == 0) {
     gecco::g_epi_skip = value;
+    return GECCO_OK;
+  }
+  if (name != nullptr && strcmp(name, "fast_epilogue") == 0) {
+    gecco::set_fast_epilogue_option(value);
+    return GECCO_OK;
+  }
+  if (name != nullptr && strcmp(name, "anorm") == 0) {
+    gecco::set_anorm_option(value);
     return GECCO_OK;
   }
   if (name != nullptr && strcmp(name, "graphs") == 0) {

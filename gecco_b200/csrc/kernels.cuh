@@ -17,9 +17,14 @@ int make_residual_tmap(const float* res, long long ldr, int m, int n_out, const 
 // Returns GECCO_OK and sets *handled = 1 when the problem fits, *handled = 0 when the caller must use launch_gemm's
 // single-CTA kernel.
 int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t s, int* handled);
+// A-operand AdaGN (gecco_anorm) is available for this shape (CTA-pair kernel, k % 64 == 0) and the pair kernel is enabled.
+bool gemm_anorm_supported(int m, int rows_per_cloud, int n_out, int k);
+bool g_use_pairs_ref();
+void set_fast_epilogue_option(int value);  // gemm_pair.cu: gecco_set_option("fast_epilogue", v)
 
 int launch_gemm(const gecco_gemm_args& a, cudaStream_t s);
-void set_graphs_option(int value);  // engine.cu: gecco_set_option("graphs", v)
+void set_graphs_option(int value);
+void set_anorm_option(int value);  // engine.cu: gecco_set_option("anorm", v)  // engine.cu: gecco_set_option("graphs", v)
 // Fused MLP (mlp_fused.cu): GEMM -> Gaussian activation -> GEMM -> + residual with the hidden tensor on chip.
 bool mlp_fused_supported(const gecco_mlp_args& a);
 int launch_mlp_fused(const gecco_mlp_args& a, cudaStream_t s);

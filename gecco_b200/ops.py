@@ -51,10 +51,14 @@ def gemm(
     sigma_stride: int = 0,
     wx: Tensor | None = None,
     sigma_data: float = 1.0,
+    anorm: dict | None = None,
 ):
-    """out = epilogue(a @ w.T) on the tcgen05 tensor cores; see gecco_gemm in include/gecco_b200.h."""
+    """out = epilogue(a @ w.T) on the tcgen05 tensor cores; see gecco_gemm in include/gecco_b200.h.
+    anorm = dict(stats f64 [clouds, K/stat_gs, 2], t fp32 [clouds], scale_w, scale_b, bias_w, bias_b, groups, stat_gs=12,
+    eps=1e-5): `a` is the un-normalised bf16 tensor and AdaGN is applied to it inside the kernel."""
+    assert a.dtype == torch.bfloat16
     lib = _lib_for(a)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     m, k = a.shape
     if n_out is None:
@@ -74,6 +78,12 @@ def gemm(
         out_bf16 = None
     args = _abi.GemmArgs()
     args.a, args.lda = a.data_ptr(), a.stride(0)
+    if anorm is not None:
+        n = args.anorm
+        n.stats, n.stat_gs, n.groups, n.eps = anorm["stats"].data_ptr(), anorm.get("stat_gs", STAT_GS), anorm["groups"], anorm.get("eps", 1e-5)
+        n.t, n.t_stride = anorm["t"].data_ptr(), 1
+        n.scale_w, n.scale_b = anorm["scale_w"].data_ptr(), anorm["scale_b"].data_ptr()
+        n.bias_w, n.bias_b = anorm["bias_w"].data_ptr(), anorm["bias_b"].data_ptr()
     args.w, args.ldw = w.data_ptr(), w.stride(0)
     args.m, args.n_out, args.k = m, n_out, k
     args.rows_per_cloud, args.valid_rows, args.w_rows_per_cloud = rows_per_cloud, valid_rows, w_rows_per_cloud
@@ -100,6 +110,15 @@ def gemm(
         args.sigma_data = sigma_data
     _abi.check(lib.gecco_gemm(C.byref(args), _stream(a)))
     return out_f32, out_bf16
+
+
+def gemm_anorm_supported(m: int, rows_per_cloud: int, n_out: int, k: int) -> bool:
+    return bool(_abi.load().gecco_gemm_anorm_supported(m, rows_per_cloud, n_out, k))
+
+
+def set_option(name: str, value: int) -> None:
+    """gecco_set_option: "gemm_pairs", "graphs", "anorm" (see include/gecco_b200.h)."""
+    _abi.check(_abi.load().gecco_set_option(name.encode(), C.c_int(int(value))))
 
 
 def mlp(a: Tensor, w1: Tensor, b1: Tensor, act_alpha: float, w2: Tensor, b2: Tensor, res: Tensor, *,

@@ -40,7 +40,9 @@ int gecco_init(int device);
 
 /* Tuning switches.  "gemm_pairs" (default 1): use the CTA-pair (cta_group::2) GEMM where it applies;
  * "graphs" (default 1, or GECCO_GRAPHS=0 in the environment): gecco_sample captures its launch sequence into a
- * CUDA graph on the first call with a given argument set and replays it afterwards. */
+ * CUDA graph on the first call with a given argument set and replays it afterwards;
+ * "anorm" (default 1, or GECCO_ANORM=0): the engine normalises (AdaGN) inside the consuming projection where the shape
+ * allows (gecco_anorm) instead of folding the normalisation into per-cloud weights. */
 int gecco_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------
@@ -61,6 +63,20 @@ int gecco_set_option(const char* name, int value);
  * Rows are grouped in clouds of rows_per_cloud rows of which the first valid_rows
  * are real points (the rest is padding, excluded from stats).
  * ------------------------------------------------------------------------ */
+/* AdaGN applied to the A operand inside the projection (models/normalization.py:36-44 in front of an nn.Linear,
+ * set_transformer.py:49,112,162,165): when stats != NULL, `a` is the UN-normalised bf16 tensor x [M, K] and the kernel
+ * multiplies by
+ *     bf16( scale_b(t)[k] * (x[m,k] - mean[b,g]) * rstd[b,g] + bias_b(t)[k] )
+ * (fp32 arithmetic, one rounding), rewriting each operand tile in shared memory before the tensor core reads it.
+ * mean / rstd come from stats (double [clouds][K/stat_gs][2] sums over the valid rows, as written by a producing
+ * epilogue), groups = number of normalisation groups, t[cloud*t_stride] the noise embedding, scale/bias the two
+ * nn.Linear(1, K) of AdaGN.  Supported where gecco_gemm_anorm_supported() says so (CTA-pair kernel shapes). */
+typedef struct gecco_anorm {
+  const double* stats; int32_t stat_gs; int32_t groups; float eps;
+  const float* t; int32_t t_stride;
+  const float* scale_w; const float* scale_b; const float* bias_w; const float* bias_b;
+} gecco_anorm;
+
 typedef struct gecco_gemm_args {
   const void* a;   int64_t lda;
   const void* w;   int64_t ldw;
@@ -77,9 +93,14 @@ typedef struct gecco_gemm_args {
   const float* geom;        /* [clouds, valid_rows, 3] fp32 raw sampler state x (not yet scaled by c_in) */
   const float* sigma; int32_t sigma_stride; float sigma_data; /* sigma[cloud*sigma_stride] */
   const float* wx;          /* [n_out, 3] fp32 */
+  gecco_anorm anorm;        /* anorm.stats == NULL: `a` is used as it is */
 } gecco_gemm_args;
 
 int gecco_gemm(const gecco_gemm_args* args, void* stream);
+/* 1 when gecco_gemm accepts args->anorm for this problem shape (m % 256 == 0, m >= 2048, rows_per_cloud % 256 == 0,
+ * k % 64 == 0, k <= 384, n_out % 96 == 0), else 0: the caller then applies AdaGN separately (gecco_adagn or
+ * gecco_fold_adagn). */
+int gecco_gemm_anorm_supported(int32_t m, int32_t rows_per_cloud, int32_t n_out, int32_t k);
 
 /* ------------------------------------------------------------------------
  * Fused point-side MLP with residual (BroadcastingLayer.forward, models/set_transformer.py:165-166;

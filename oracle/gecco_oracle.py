@@ -244,6 +244,35 @@ def sample_stochastic(cfg: OracleConfig, sd: dict, shape, features=None, K=None,
     return diffusion_to_data(cfg, sd, x_next, K)
 
 
+@torch.no_grad()
+def sample_stochastic_device(cfg: OracleConfig, sd: dict, shape, features=None, K=None, device="cuda", seed: int = 42, **kw):
+    """`sample_stochastic` with state, noise and sigma on `device` (bench.py's PyTorch-eager-on-GPU arm): the same loop,
+    draws from a generator of that device."""
+    k = {**cfg.sampler, "sigma_max": cfg.sigma_max, **kw}
+    n, S_churn, S_min, S_max, S_noise = k["num_steps"], k["S_churn"], k["S_min"], k["S_max"], k["S_noise"]
+    rng = torch.Generator(device).manual_seed(seed)
+    B = shape[0]
+    latents = torch.randn(shape, generator=rng, dtype=torch.float32, device=device)
+    ts = t_steps(n, k["sigma_max"], k["sigma_min"], k["rho"]).tolist()
+    x_next = latents.to(torch.float64) * ts[0]
+    for i, (t_cur, t_next) in enumerate(zip(ts[:-1], ts[1:])):
+        x_cur = x_next
+        gamma = min(S_churn / n, math.sqrt(2.0) - 1) if S_min <= t_cur <= S_max else 0
+        t_hat = t_cur + gamma * t_cur
+        noise = torch.randn(x_cur.shape, generator=rng, dtype=torch.float32, device=device)
+        x_hat = x_cur + math.sqrt(t_hat**2 - t_cur**2) * S_noise * noise
+        sig = torch.full((B,), t_hat, device=device, dtype=torch.float32)
+        den = denoise(cfg, sd, x_hat.float(), sig, features, K).to(torch.float64)
+        d_cur = (x_hat - den) / t_hat
+        x_next = x_hat + (t_next - t_hat) * d_cur
+        if i < n - 1:
+            sig = torch.full((B,), t_next, device=device, dtype=torch.float32)
+            den = denoise(cfg, sd, x_next.float(), sig, features, K).to(torch.float64)
+            d_prime = (x_next - den) / t_next
+            x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
+    return diffusion_to_data(cfg, sd, x_next, K)
+
+
 # diffusion.py:354-470
 @torch.no_grad()
 def upsample(cfg: OracleConfig, sd: dict, data: Tensor, n_new: int | None = None, new_latents: Tensor | None = None,

@@ -258,8 +258,8 @@ def bench_shape():
                 feats = model.conditioner(ctx).features
             out["pyramid_sub"] = [f[:, ::8, ::3, ::3].contiguous() for f in feats]
             out["pyramid_rms"] = [f.pow(2).mean().sqrt().item() for f in feats]
-        x = torch.randn(B, N, 3, generator=synth.gen(51)) * sp["x_scale"]
         sig = torch.tensor(sp["noise_sigma"])
+        x = synth.noisy_input(B, N, sig, 51, 54)  # the EDM input distribution: unit-variance data + sigma * noise
         with torch.no_grad():
             D, hs = model(x, sig, ctx, do_cache=True)
         out["D"], out["hs_sub"] = D, [sub(h) for h in hs]
@@ -290,7 +290,7 @@ def bench_shape():
         out["sample64"] = samp
         print(sp["name"], "tame 64-step sampler: bf16 drift of the reference (diffusion space)", drift["sample64"],
               "finite", torch.isfinite(to_diff(samp)).all().item())
-        recipe = {**common, **{k: v for k, v in sp.items() if k != "name"}, "B": B, "N": N, "x_seed": 51, "ex_seed": 52,
+        recipe = {**common, **{k: v for k, v in sp.items() if k != "name"}, "B": B, "N": N, "x_seed": 51, "x_noise_seed": 54, "ex_seed": 52,
                   "loss_seed": 53, "sample_B": Bs, "sample_seed": 61, "sample_steps": 64}
         recipe["noise_sigma"] = sig
         torch.save(dict(recipe=recipe, drift=drift, **out), OUT / (sp["name"] + ".pt"))

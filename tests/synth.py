@@ -127,6 +127,14 @@ def tame(sd: Dict[str, torch.Tensor], out_scale: float) -> Dict[str, torch.Tenso
     return out
 
 
+def noisy_input(batch: int, points: int, sigma: torch.Tensor, data_seed: int, noise_seed: int) -> torch.Tensor:
+    """What the denoiser sees in the sampler and in the training loss (diffusion.py:139-140, 325): diffusion-space data of
+    unit variance plus sigma * noise, so that c_in(sigma) * x has unit variance at every noise level."""
+    x0 = torch.randn(batch, points, 3, generator=gen(data_seed))
+    n = torch.randn(batch, points, 3, generator=gen(noise_seed))
+    return x0 + sigma.reshape(-1, 1, 1) * n
+
+
 def synth_features(batch: int, sizes: Sequence[int], seed: int, dims: Sequence[int] = CONTEXT_DIMS):
     """Synthetic feature pyramid (what ConvNeXtExtractor would return, models/feature_pyramid.py:62-73): NCHW fp32."""
     g = gen(seed)

@@ -60,8 +60,8 @@ def test_forward_and_loss_at_bench_shape(cuda, monkeypatch, name):
             e = rms(f[:, ::8, ::3, ::3].cpu() - sub) / frms
             print(f"{name}: ConvNeXt level {l} rel rms vs reference {e:.2e}")
             assert e < 1e-3, (l, e)
-    x = torch.randn(B, N, 3, generator=synth.gen(r["x_seed"])) * r["x_scale"]
     sig = r["noise_sigma"]
+    x = synth.noisy_input(B, N, sig, r["x_seed"], r["x_noise_seed"])
     D, hs = model(x.to(cuda), sig.to(cuda), ctx, do_cache=True)
     check_F(D, g["D"], x, sig, name + " D")
     for l, (h, hg) in enumerate(zip(hs, g["hs_sub"])):
@@ -114,3 +114,25 @@ def test_full_sampler_tame_weights(cuda, name):
     # a second call replays the captured graph and reproduces the first bit for bit
     s2 = model.sample_stochastic((Bs, N, 3), ctx_s, rng=synth.gen(r["sample_seed"]), num_steps=r["sample_steps"])
     assert eng.graph_status() == 2 and torch.equal(s, s2)
+
+
+def test_anorm_and_fold_paths_agree(cuda):
+    """AdaGN inside the consuming GEMM (A-operand transform, default at this shape) against the per-cloud weight fold
+    (`gecco_set_option("anorm", 0)`): two implementations of the same arithmetic, both within tolerance of the reference."""
+    from gecco_b200 import ops
+
+    g, r, model, ctx = _setup("bench_cond_gaussian", cuda)
+    sig = r["noise_sigma"]
+    x = synth.noisy_input(r["B"], r["N"], sig, r["x_seed"], r["x_noise_seed"])
+    try:
+        ops.set_option("anorm", 0)
+        D_fold = model(x.to(cuda), sig.to(cuda), ctx).clone()
+        ops.set_option("anorm", 1)
+        D_an = model(x.to(cuda), sig.to(cuda), ctx).clone()
+    finally:
+        ops.set_option("anorm", 1)
+    check_F(D_fold, g["D"], x, sig, "fold path")
+    check_F(D_an, g["D"], x, sig, "anorm path")
+    assert not torch.equal(D_fold, D_an)  # they really are two code paths
+    e_fold, e_an = rms(D_fold.cpu() - g["D"]), rms(D_an.cpu() - g["D"])
+    print(f"rms error vs reference: fold {e_fold:.3e}, anorm {e_an:.3e}")

@@ -184,3 +184,82 @@ def test_gemm_pair_percloud_act(cuda, pairs):
         got = o16[b * Np:b * Np + N].float()
         assert (got - ref).abs().max().item() < 4e-2, b
         assert o16[b * Np + N:(b + 1) * Np].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n_out,act", [(1152, None), (768, 1.3), (384, None)])
+@pytest.mark.parametrize("clouds,rows_per_cloud,valid", [(3, 768, 700), (16, 2048, 2048)])
+def test_gemm_anorm_operand(cuda, n_out, act, clouds, rows_per_cloud, valid):
+    """AdaGN applied to the A operand inside the CTA-pair GEMM (gecco_anorm): bf16 x -> a * x + s in fp32 -> bf16, in place
+    in shared memory -> tcgen05, against AdaGN in torch (models/normalization.py:36-44) of the same bf16 x followed by
+    the same bf16 projection."""
+    import torch.nn.functional as F
+
+    from gecco_b200 import ops
+
+    K, groups = 384, 32
+    m = clouds * rows_per_cloud
+    assert ops.gemm_anorm_supported(m, rows_per_cloud, n_out, K)
+    g = torch.Generator(device="cpu").manual_seed(n_out + clouds)
+    x = (torch.randn(clouds, rows_per_cloud, K, generator=g) * 0.7 + torch.randn(1, 1, K, generator=g) * 1.5).to(cuda)
+    x[:, valid:] = 0.0  # padding rows of the residual stream are zeros
+    x = x.bfloat16().float()  # the operand the kernel reads is the bf16 copy of the residual stream
+    x2 = x.view(m, K)
+    w = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    bias = torch.randn(n_out, generator=g).to(cuda)
+    t = (torch.randn(clouds, generator=g) * 0.8).to(cuda)
+    sw, sb = (torch.randn(K, 1, generator=g) * 0.3).to(cuda), (torch.randn(K, generator=g) * 0.1 + 1).to(cuda)
+    bw, bb = (torch.randn(K, 1, generator=g) * 0.3).to(cuda), (torch.randn(K, generator=g) * 0.1).to(cuda)
+    stats = ops.group_stats(x2, rows_per_cloud, valid, 12)
+    _, o16 = ops.gemm(x2.bfloat16(), w, bias=bias, act_alpha=act, out_bf16=True, rows_per_cloud=rows_per_cloud, valid_rows=valid,
+                      anorm=dict(stats=stats, t=t, scale_w=sw, scale_b=sb, bias_w=bw, bias_b=bb, groups=groups))
+    torch.cuda.synchronize()
+    xv = x[:, :valid]
+    normed = F.group_norm(xv.transpose(1, 2), groups, eps=1e-5).transpose(1, 2)
+    y = (t[:, None, None] * sw[:, 0] + sb) * normed + (t[:, None, None] * bw[:, 0] + bb)
+    ref = _ref(y.bfloat16().reshape(-1, K), w, bias=bias, alpha=act).view(clouds, valid, n_out)
+    got = o16.view(clouds, rows_per_cloud, n_out)[:, :valid].float()
+    err = (got - ref).pow(2).mean().sqrt().item() / ref.pow(2).mean().sqrt().item()
+    # bf16 output rounding (2^-9) plus the few operand elements that round to the neighbouring bf16 value
+    assert err < 4e-3, err
+    assert got.isfinite().all()
+    if valid < rows_per_cloud:  # padding rows come out as exact zeros
+        assert o16.view(clouds, rows_per_cloud, n_out)[:, valid:].abs().max().item() == 0.0
+    # the same call is rejected, loudly, where the kernel cannot take it
+    assert not ops.gemm_anorm_supported(1024, 512, n_out, K) and not ops.gemm_anorm_supported(m, rows_per_cloud, n_out, 136)
+    with pytest.raises(ValueError):
+        ops.gemm(x2[: 3 * 384].bfloat16(), w, out_bf16=True, rows_per_cloud=384, valid_rows=300,
+                 anorm=dict(stats=stats, t=t, scale_w=sw, scale_b=sb, bias_w=bw, bias_b=bb, groups=groups))
+
+
+@pytest.mark.parametrize("n_out,act", [(1152, None), (768, 1.3)])
+@pytest.mark.parametrize("clouds,rows_per_cloud,valid", [(4, 768, 700), (8, 2048, 2048)])
+def test_gemm_fast_epilogue_is_bit_identical(cuda, n_out, act, clouds, rows_per_cloud, valid):
+    """The bf16-only fast epilogue of the CTA-pair kernel (three TMEM chunks in flight, early accumulator release, one
+    bulk group per tile) against the generic epilogue: same arithmetic per element, so the outputs must agree bit for
+    bit; both are also checked against torch."""
+    from gecco_b200 import ops
+
+    K = 384
+    m = clouds * rows_per_cloud
+    g = torch.Generator(device="cpu").manual_seed(n_out + rows_per_cloud)
+    a = torch.randn(m, K, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(clouds * n_out, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    bias = torch.randn(clouds, n_out, generator=g).to(cuda)
+    outs = []
+    try:
+        for fast in (0, 1):
+            ops.set_option("fast_epilogue", fast)
+            out = torch.full((m, n_out), 3.0, device=cuda, dtype=torch.bfloat16)
+            ops.gemm(a, w, bias=bias, bias_stride=n_out, act_alpha=act, out_bf16=out, rows_per_cloud=rows_per_cloud, valid_rows=valid,
+                     w_rows_per_cloud=n_out, n_out=n_out)
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        ops.set_option("fast_epilogue", 1)
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    got = outs[1].view(clouds, rows_per_cloud, n_out)
+    for c in range(clouds):
+        ref = _ref(a.view(clouds, rows_per_cloud, K)[c, :valid], w.view(clouds, n_out, K)[c], bias=bias[c], alpha=act)
+        assert (got[c, :valid].float() - ref).abs().max().item() < 6e-2
+    if valid < rows_per_cloud:
+        assert got[:, valid:].abs().max().item() == 0.0

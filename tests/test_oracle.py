@@ -114,7 +114,7 @@ def test_bench_shape_goldens(name):
         for f, sub in zip(feats, g["pyramid_sub"]):
             assert rel(f[:, ::8, ::3, ::3], sub) < TOL
         K = synth.camera(B, r["K"])
-    x = torch.randn(B, N, 3, generator=synth.gen(r["x_seed"])) * r["x_scale"]
+    x = synth.noisy_input(B, N, r["noise_sigma"], r["x_seed"], r["x_noise_seed"])
     with torch.no_grad():
         D, hs = O.denoise(cfg, sd, x, r["noise_sigma"], feats, K, return_h=True)
     assert rel(D, g["D"]) < 5e-5

@@ -1,0 +1,10 @@
+#!/bin/bash
+python -m pytest tests/test_gemm_gpu.py tests/test_bench_shape_gpu.py -m gpu -q > gpurun_out/r2d_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/r2d_pytest.log | tail -10
+python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/r2d_bench.json 2> gpurun_out/r2d_bench.err; echo "bench rc=$?"; python - <<'PY'
+import json
+j=json.load(open('gpurun_out/r2d_bench.json'))
+print({k:j[k] for k in ('value','ms_per_step','host_enqueue_ms_per_step','cuda_graph')})
+for c in j['kernel_classes']: print(c['name'], c['ms'], c['tflops'], c['gbs'])
+PY
+GECCO_DEBUG_COUNTERS=1 python -m gecco_b200.build > /dev/null 2>&1
+CASES=kvq_anorm,mlp_up_anorm python tools/gemm_cycles.py > gpurun_out/r2e_gemm_cycles.log 2>&1; cat gpurun_out/r2e_gemm_cycles.log
