@@ -217,6 +217,18 @@ class SampleArgs(C.Structure):
     ]
 
 
+class UpsampleStepArgs(C.Structure):
+    _fields_ = [
+        ("clouds", C.c_int32), ("seed_points", C.c_int32), ("new_points", C.c_int32), ("num_substeps", C.c_int32),
+        ("last_step", C.c_int32),
+        ("t_cur", C.c_double), ("t_next", C.c_double), ("gamma", C.c_double), ("s_noise", C.c_double),
+        ("seed_data", C.c_void_p), ("seed_noise", C.c_void_p), ("noise", C.c_void_p),
+        ("x", C.c_void_p),
+        ("ctx", Context),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 class ProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -251,6 +263,9 @@ def load() -> C.CDLL:
     lib.gecco_destroy.argtypes = [C.c_void_p]
     lib.gecco_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gecco_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gecco_upsample_workspace_bytes.restype = C.c_int64
+    lib.gecco_upsample_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.gecco_upsample_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gecco_graph_status.argtypes = [C.c_void_p]
     lib.gecco_graph_status.restype = C.c_int
     _lib = lib

@@ -689,6 +689,38 @@ int launch_head(const gecco_head_args& a, cudaStream_t s) {
   return GECCO_OK;
 }
 
+// Upsampling helpers (diffusion.py:430-437, 447-449, 464-466).  torch evaluates `0-dim float64 * float32 tensor` in fp32,
+// so the noise products are fp32 and only the accumulation into the sampler state is float64.
+__global__ void seed_renoise_kernel(const float* __restrict__ data, const float* __restrict__ noise, float t, long long n,
+                                    float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(data[i], __fmul_rn(noise[i], t));  // data + randn * t_cur, two roundings like torch
+}
+// x_hat = (src [+ c1 * n1]) + c2 * n2: re-noising of the previous sub-step (optional) followed by the churn of this one.
+__global__ void substep_noise_kernel(const double* __restrict__ src, const float* __restrict__ n1, float c1,
+                                     const float* __restrict__ n2, float c2, long long n, double* __restrict__ x_hat,
+                                     float* __restrict__ xin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = src[i];
+  if (n1 != nullptr) x = x + static_cast<double>(__fmul_rn(c1, n1[i]));
+  if (n2 != nullptr) x = x + static_cast<double>(__fmul_rn(c2, n2[i]));
+  x_hat[i] = x;
+  xin[i] = static_cast<float>(x);
+}
+
+int launch_seed_renoise(const float* data, const float* noise, float t, long long n, float* out, cudaStream_t s) {
+  seed_renoise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(data, noise, t, n, out);
+  GECCO_CHECK_LAUNCH("seed_renoise_kernel");
+  return GECCO_OK;
+}
+int launch_substep_noise(const double* src, const float* n1, float c1, const float* n2, float c2, long long n, double* x_hat,
+                         float* xin, cudaStream_t s) {
+  substep_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, n1, c1, n2, c2, n, x_hat, xin);
+  GECCO_CHECK_LAUNCH("substep_noise_kernel");
+  return GECCO_OK;
+}
+
 int launch_sampler_init(const float* latents, const float* noise, double t0, double churn, long long n, double* x_hat,
                         float* xin, cudaStream_t s) {
   sampler_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(latents, noise, t0, churn, n, x_hat, xin);

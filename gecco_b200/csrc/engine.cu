@@ -265,14 +265,18 @@ gecco_fold_adagn_args fold_base(const gecco_engine* e, const float* const* nw /*
 // bench shape the fused kernel (446 us / layer) is still slower than the two pair GEMMs (253 us / layer), see DESIGN.md.
 // gecco_set_option("anorm", 0) / GECCO_ANORM=0 keeps the AdaGN -> per-cloud weight fold path everywhere (A/B measurements,
 // tests of the fold path at shapes where the A-operand transform would otherwise be taken).
+// (Measured and dropped: reading the fp32 stream instead of its bf16 copy -- through a TMA staging ring or straight from
+// global memory in the normalising warps -- saves the producers' bf16 write but starves the resident-tile pipeline: the
+// k|v|q projection went from 143 to 170-250 us.)
 int g_anorm_enabled = -1;
-bool anorm_enabled() {
+int anorm_mode() {
   if (g_anorm_enabled < 0) {
     const char* v = getenv("GECCO_ANORM");
     g_anorm_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
   }
-  return g_anorm_enabled != 0;
+  return g_anorm_enabled;
 }
+bool anorm_enabled() { return anorm_mode() != 0; }
 
 bool fused_mlp_enabled() {
   static const bool on = [] {
@@ -315,6 +319,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
   // the shape allows, else folded into per-cloud weights (fold_adagn + bf16 copy xb of the residual stream).
   const bool an = anorm_enabled() && !fused_mlp_enabled() && gemm_anorm_supported(rows, Np, C, C) &&
                   gemm_anorm_supported(rows, Np, 3 * C, C) && gemm_anorm_supported(rows, Np, hid, C);
+  constexpr bool an32 = false;
   __nv_bfloat16* const xb_out = w.xb;  // bf16 copy of the residual stream: the (un-normalised) operand of both paths
   auto set_anorm = [&](gecco_gemm_args& g, const float* const* nw, const double* st) {
     g.anorm.stats = st; g.anorm.stat_gs = C / sg; g.anorm.groups = sg; g.anorm.eps = 1e-5f;
@@ -394,7 +399,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       set_anorm(g, lw + GECCO_LW_BN, stat(l, 0));
       g.bias = L.bcat + r0; g.bias_stride = 0;
       g.out_bf16 = w.big + r0; g.ldo16 = C3;
-      TRYP(K_GEMM_KVQ, 2 * Mv * Cd * (C3 - r0), Mv * (Cd * 2 + (C3 - r0) * 2.0) + 2.0 * (C3 - r0) * Cd, launch_gemm(g, s));
+      TRYP(K_GEMM_KVQ, 2 * Mv * Cd * (C3 - r0), Mv * (Cd * (an32 ? 4 : 2) + (C3 - r0) * 2.0) + 2.0 * (C3 - r0) * Cd, launch_gemm(g, s));
     } else {
       gecco_fold_adagn_args f = fold_base(e, lw + GECCO_LW_BN, stat(l, 0), w.c_noise, clouds, points);
       f.w = L.wcat + (size_t)r0 * C; f.ldw = C; f.bias = L.bcat + r0; f.n_out = C3 - r0;
@@ -461,7 +466,7 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
       g.out_bf16 = xb_out; g.ldo16 = C;
       g.stats = stat(l, 3);
-      TRYP(K_GEMM_UNPOOL_OUT, 2 * Mv * Cd * Cd, Mv * Cd * 12 + 2 * Cd * Cd, launch_gemm(g, s));
+      TRYP(K_GEMM_UNPOOL_OUT, 2 * Mv * Cd * Cd, Mv * Cd * (an32 ? 10 : 12) + 2 * Cd * Cd, launch_gemm(g, s));
     }
     // x = x + mlp(AdaGN_mlp(x, t))  (:165-166): mlp_norm folded into mlp.0; statistics for the next broadcast_norm /
     // the head norm
@@ -471,13 +476,13 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       set_anorm(g, lw + GECCO_LW_MN, stat(l, 3));
       g.bias = lw[GECCO_LW_MLP_B0]; g.bias_stride = 0; g.act = 1; g.act_alpha = L.mlp_alpha;
       g.out_bf16 = w.big; g.ldo16 = hid;
-      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd * 2 + Hd * 2) + 2.0 * Cd * Hd, launch_gemm(g, s));
+      TRYP(K_GEMM_MLP0, 2 * Mv * Cd * Hd, Mv * (Cd * (an32 ? 4 : 2) + Hd * 2) + 2.0 * Cd * Hd, launch_gemm(g, s));
       g = gemm_base(w.big, hid, L.mlp_w2, hid, rows, C, hid, Np, points);
       g.bias = lw[GECCO_LW_MLP_B2];
       g.res = w.x; g.ldr = C; g.out_f32 = w.x; g.ldo32 = C;
-      g.out_bf16 = w.xb; g.ldo16 = C;
+      g.out_bf16 = xb_out; g.ldo16 = C;
       g.stats = next_stats;
-      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * 10) + 2 * Cd * Hd, launch_gemm(g, s));
+      TRYP(K_GEMM_MLP2, 2 * Mv * Cd * Hd, Mv * (Hd * 2 + Cd * (an32 ? 8 : 10)) + 2 * Cd * Hd, launch_gemm(g, s));
     } else {
       gecco_fold_adagn_args f = fold_base(e, lw + GECCO_LW_MN, stat(l, 3), w.c_noise, clouds, points);
       f.w = lw[GECCO_LW_MLP_W0]; f.ldw = C; f.bias = lw[GECCO_LW_MLP_B0]; f.n_out = hid;
@@ -714,7 +719,8 @@ int enqueue_sample(gecco_engine* e, const gecco_sample_args* a, cudaStream_t s) 
     return sqrt(t_hat * t_hat - t[i] * t[i]) * a->s_noise;
   };
   // x_hat_0 = latents * t_0 + churn_0 * noise_0  (:308, :325)
-  TRY(launch_sampler_init(a->latents, a->noise, t[0], churn(0), n3, w.x_hat, w.xin_a, s));
+  // (a zero churn factor skips the noise read altogether: the deterministic sampler never touches the noise buffer)
+  TRY(launch_sampler_init(a->latents, churn(0) != 0.0 ? a->noise : nullptr, t[0], churn(0), n3, w.x_hat, w.xin_a, s));
   for (int i = 0; i < a->num_steps; ++i) {
     const double t_hat = t[i] + a->host_gamma[i] * t[i];
     const double t_next = t[i + 1];
@@ -726,8 +732,8 @@ int enqueue_sample(gecco_engine* e, const gecco_sample_args* a, cudaStream_t s) 
     if (i < a->num_steps - 1) {  // Heun (:339-347) + churn of step i+1
       h.mode = 3;
       h.xin_next = w.xin_a;
-      h.noise_next = a->noise + (size_t)(i + 1) * n3;
       h.churn_next = churn(i + 1);
+      h.noise_next = h.churn_next != 0.0 ? a->noise + (size_t)(i + 1) * n3 : nullptr;
       TRY(run_eval(e, w, w.xin_b, nullptr, 0, (float)t_next, nullptr, 0, a->clouds, a->points, a->ctx, nullptr, nullptr, h, s));
     }
   }
@@ -748,12 +754,13 @@ std::vector<unsigned char> sample_key(const gecco_sample_args* a) {
   put(&a->latents, sizeof(void*)); put(&a->noise, sizeof(void*)); put(&a->x_out, sizeof(void*));
   put(&a->ctx, sizeof(gecco_context));
   put(&a->workspace, sizeof(void*)); put(&a->workspace_bytes, sizeof(int64_t));
-  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_enabled() ? 2 : 0);
+  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1);
   put(&fused, sizeof(int));
   return k;
 }
 
-constexpr size_t kMaxSampleGraphs = 4;
+// sampler loops (one graph per argument set) and upsampling steps (one graph per noise level: 64 per schedule)
+constexpr size_t kMaxGraphs = 160;
 
 void drop_graph(gecco_engine* e, size_t i) {
   cudaGraphExecDestroy(e->graphs[i].exec);
@@ -765,24 +772,24 @@ void set_graphs_option(int value) { g_graphs_enabled = value != 0 ? 1 : 0; }
 void set_anorm_option(int value) { g_anorm_enabled = value != 0 ? 1 : 0; }
 }  // namespace gecco
 
-extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* stream) {
-  GECCO_REQUIRE(a != nullptr, "gecco_sample: null args");
-  TRY(check_common(e, a->clouds, a->points, a->ctx, a->workspace, a->workspace_bytes));
-  GECCO_REQUIRE(a->num_steps >= 1 && a->host_t_steps && a->host_gamma, "gecco_sample: schedule missing");
-  GECCO_REQUIRE(a->latents && a->noise && a->x_out, "gecco_sample: latents / noise / output missing");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+namespace gecco {
+namespace {
+// Runs `enqueue(stream)` through the engine's CUDA-graph cache: captured on the engine's own stream the first time `key`
+// is seen (forked from / joined to the caller's stream with events, so the legacy default stream works too), replayed
+// afterwards.  Falls back to a plain enqueue when graphs are off, while profiling, or when the caller's stream is itself
+// being captured.
+template <typename Enqueue>
+int run_graphed(gecco_engine* e, const std::vector<unsigned char>& key, cudaStream_t s, Enqueue enqueue) {
   e->last_graph_status = 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (s != nullptr && s != cudaStreamLegacy) cudaStreamIsCapturing(s, &cap);
-  if (!graphs_enabled() || g_prof.on || cap != cudaStreamCaptureStatusNone) return enqueue_sample(e, a, s);
-
+  if (!graphs_enabled() || g_prof.on || cap != cudaStreamCaptureStatusNone) return enqueue(s);
   if (e->gstream == nullptr) {
     cudaError_t ce = cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
-    if (ce != cudaSuccess) return fail_cuda(ce, "gecco_sample: graph stream / events");
+    if (ce != cudaSuccess) return fail_cuda(ce, "graph stream / events");
   }
-  const std::vector<unsigned char> key = sample_key(a);
   size_t hit = e->graphs.size();
   for (size_t i = 0; i < e->graphs.size(); ++i)
     if (e->graphs[i].key == key) { hit = i; break; }
@@ -790,8 +797,8 @@ extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* s
     // capture (thread-local mode: other threads' CUDA calls neither join nor invalidate it)
     const long long before = g_launches;
     cudaError_t ce = cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal);
-    if (ce != cudaSuccess) return fail_cuda(ce, "gecco_sample: cudaStreamBeginCapture");
-    const int rc = enqueue_sample(e, a, e->gstream);
+    if (ce != cudaSuccess) return fail_cuda(ce, "cudaStreamBeginCapture");
+    const int rc = enqueue(e->gstream);
     cudaGraph_t graph = nullptr;
     ce = cudaStreamEndCapture(e->gstream, &graph);
     const long long launches = g_launches - before;
@@ -801,12 +808,13 @@ extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* s
     if (graph != nullptr) cudaGraphDestroy(graph);
     if (rc != GECCO_OK) return rc;  // argument errors surface exactly as in the eager path
     if (ce != cudaSuccess || exec == nullptr) {
-      // a driver that cannot capture this launch sequence: run eagerly, visibly (gecco_last_graph_status < 0)
+      // a driver that cannot capture this launch sequence: run eagerly, visibly (gecco_graph_status < 0)
       cudaGetLastError();
+      const int rc2 = enqueue(s);
       e->last_graph_status = -1;
-      return enqueue_sample(e, a, s);
+      return rc2;
     }
-    if (e->graphs.size() >= kMaxSampleGraphs) {
+    if (e->graphs.size() >= kMaxGraphs) {
       size_t oldest = 0;
       for (size_t i = 1; i < e->graphs.size(); ++i)
         if (e->graphs[i].stamp < e->graphs[oldest].stamp) oldest = i;
@@ -825,10 +833,123 @@ extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* s
   if (ce == cudaSuccess) ce = cudaGraphLaunch(g.exec, e->gstream);
   if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_join, e->gstream);
   if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, e->ev_join, 0);
-  if (ce != cudaSuccess) return fail_cuda(ce, "gecco_sample: graph launch");
+  if (ce != cudaSuccess) return fail_cuda(ce, "graph launch");
   g_launches += g.launches;
   return GECCO_OK;
 }
+}  // namespace
+}  // namespace gecco
+
+extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* stream) {
+  GECCO_REQUIRE(a != nullptr, "gecco_sample: null args");
+  TRY(check_common(e, a->clouds, a->points, a->ctx, a->workspace, a->workspace_bytes));
+  GECCO_REQUIRE(a->num_steps >= 1 && a->host_t_steps && a->host_gamma, "gecco_sample: schedule missing");
+  GECCO_REQUIRE(a->latents && a->x_out, "gecco_sample: latents / output missing");
+  for (int i = 0; i < a->num_steps; ++i)
+    GECCO_REQUIRE(a->noise != nullptr || a->host_gamma[i] == 0.0 || a->s_noise == 0.0, "gecco_sample: noise missing (gamma[%d] > 0)", i);
+  return run_graphed(e, sample_key(a), static_cast<cudaStream_t>(stream), [&](cudaStream_t s) { return enqueue_sample(e, a, s); });
+}
+
+// ------------------------------------------------------------------------------------------------ upsampling
+namespace gecco {
+namespace {
+struct UpsampleLayout {
+  size_t carve_bytes, cache_off, seed_in_off, seed_out_off, total;
+};
+UpsampleLayout upsample_layout(const gecco_engine* e, int clouds, int seed_points, int new_points) {
+  UpsampleLayout u;
+  const int big = seed_points > new_points ? seed_points : new_points;
+  u.carve_bytes = carve(e, clouds, big, nullptr).bytes;
+  size_t off = align_up(u.carve_bytes);
+  u.cache_off = off;
+  off = align_up(off + (size_t)e->d.n_layers * clouds * e->d.num_inducers * e->d.feature_dim * sizeof(float));
+  u.seed_in_off = off;
+  off = align_up(off + (size_t)clouds * seed_points * 3 * sizeof(float));
+  u.seed_out_off = off;
+  off = align_up(off + (size_t)clouds * seed_points * 3 * sizeof(float));
+  u.total = off;
+  return u;
+}
+}  // namespace
+}  // namespace gecco
+
+extern "C" int64_t gecco_upsample_workspace_bytes(const gecco_engine* e, int32_t clouds, int32_t seed_points, int32_t new_points) {
+  if (e == nullptr || clouds <= 0 || seed_points <= 0 || new_points <= 0) return 0;
+  return (int64_t)upsample_layout(e, clouds, seed_points, new_points).total;
+}
+
+namespace gecco {
+namespace {
+int enqueue_upsample_step(gecco_engine* e, const gecco_upsample_step_args* a, cudaStream_t s);
+}
+}  // namespace gecco
+
+extern "C" int gecco_upsample_step(gecco_engine* e, const gecco_upsample_step_args* a, void* stream) {
+  GECCO_REQUIRE(a != nullptr, "gecco_upsample_step: null args");
+  GECCO_REQUIRE(e != nullptr, "null engine handle");
+  GECCO_REQUIRE(a->seed_points > 0 && a->new_points > 0 && a->num_substeps >= 1, "gecco_upsample_step: empty problem");
+  GECCO_REQUIRE(a->seed_data && a->seed_noise && a->noise && a->x, "gecco_upsample_step: seed / noise / state missing");
+  GECCO_REQUIRE(a->t_cur > 0.0, "gecco_upsample_step: t_cur must be positive");
+  const UpsampleLayout u = upsample_layout(e, a->clouds, a->seed_points, a->new_points);
+  TRY(check_common(e, a->clouds, a->new_points, a->ctx, a->workspace, a->workspace_bytes));
+  GECCO_REQUIRE(a->workspace_bytes >= (int64_t)u.total, "workspace too small: %lld bytes given, %lld needed",
+                (long long)a->workspace_bytes, (long long)u.total);
+  // everything the launch sequence depends on (the struct holds shapes, schedule scalars and every pointer)
+  std::vector<unsigned char> key(sizeof(gecco_upsample_step_args) + 8);
+  memcpy(key.data(), a, sizeof(gecco_upsample_step_args));
+  memcpy(key.data() + sizeof(gecco_upsample_step_args), "upsample", 8);
+  key.push_back((unsigned char)((fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1)));
+  return run_graphed(e, key, static_cast<cudaStream_t>(stream), [&](cudaStream_t s) { return enqueue_upsample_step(e, a, s); });
+}
+
+namespace gecco {
+namespace {
+int enqueue_upsample_step(gecco_engine* e, const gecco_upsample_step_args* a, cudaStream_t s) {
+  const UpsampleLayout u = upsample_layout(e, a->clouds, a->seed_points, a->new_points);
+  uint8_t* base = static_cast<uint8_t*>(a->workspace);
+  float* cache = reinterpret_cast<float*>(base + u.cache_off);
+  float* seed_in = reinterpret_cast<float*>(base + u.seed_in_off);
+  float* seed_out = reinterpret_cast<float*>(base + u.seed_out_off);
+  const long long ns = (long long)a->clouds * a->seed_points * 3, n3 = (long long)a->clouds * a->new_points * 3;
+  // data_ctx = data + randn * t_cur; full evaluation on the seed cloud, inducer states cached (:430-437)
+  TRY(launch_seed_renoise(a->seed_data, a->seed_noise, (float)a->t_cur, ns, seed_in, s));
+  {
+    const Workspace ws = carve(e, a->clouds, a->seed_points, a->workspace);
+    gecco_head_args h = {};
+    h.mode = 1;
+    h.out_f32 = seed_out;  // the denoised seed cloud itself is not used (:431 `_`)
+    TRY(run_eval(e, ws, seed_in, nullptr, 0, (float)a->t_cur, nullptr, 0, a->clouds, a->seed_points, a->ctx, nullptr, cache, h, s));
+  }
+  const Workspace w = carve(e, a->clouds, a->new_points, a->workspace);
+  const double t_hat = a->t_cur + a->gamma * a->t_cur;
+  const float churn = (float)(sqrt(t_hat * t_hat - a->t_cur * a->t_cur) * a->s_noise);
+  const float redo = a->last_step ? 0.f : (float)sqrt(a->t_cur * a->t_cur - a->t_next * a->t_next);
+  const double* src = a->x;
+  for (int uu = 0; uu < a->num_substeps; ++uu) {
+    const float* n_churn = a->noise + (size_t)(a->last_step ? uu : 2 * uu) * n3;
+    const float* n_redo = (uu > 0 && !a->last_step) ? a->noise + (size_t)(2 * uu - 1) * n3 : nullptr;  // of the previous sub-step
+    TRY(launch_substep_noise(src, n_redo, redo, n_churn, churn, n3, w.x_hat, w.xin_a, s));
+    gecco_head_args h = {};
+    h.mode = 2;  // Euler (:452-454)
+    h.x_hat = w.x_hat; h.x_next = w.x_next; h.d_cur = w.d_cur; h.xin_next = w.xin_b;
+    h.t_hat = t_hat; h.t_next = a->t_next;
+    TRY(run_eval(e, w, w.xin_a, nullptr, 0, (float)t_hat, nullptr, 0, a->clouds, a->new_points, a->ctx, cache, nullptr, h, s));
+    if (!a->last_step) {  // 2nd order correction (:457-460); the result replaces x_hat
+      h.mode = 3;
+      h.xin_next = w.xin_a;
+      h.noise_next = nullptr; h.churn_next = 0.0;
+      TRY(run_eval(e, w, w.xin_b, nullptr, 0, (float)a->t_next, nullptr, 0, a->clouds, a->new_points, a->ctx, cache, nullptr, h, s));
+      src = w.x_hat;
+    } else {
+      src = w.x_next;
+    }
+  }
+  copy_f64_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(src, a->x, n3);
+  GECCO_CHECK_LAUNCH("copy_f64_kernel");
+  return GECCO_OK;
+}
+}  // namespace
+}  // namespace gecco
 
 extern "C" int gecco_graph_status(const gecco_engine* e) { return e ? e->last_graph_status : 0; }
 

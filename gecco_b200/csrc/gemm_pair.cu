@@ -465,7 +465,7 @@ int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t stream, int* handled
   // bf16-only whole-tile projections take the fast epilogue
   const bool fast = fast_epilogue_enabled() && a.res == nullptr && a.stats == nullptr && a.out_f32 == nullptr && a.geom == nullptr &&
                     a.bias != nullptr && a.out_bf16 != nullptr && a.n_out % BN == 0 &&
-                    p.e.skip == 0 && g_gemm_debug == nullptr;
+                    p.e.skip == 0;
   const int epi_bytes = (fast ? epi_fast_smem_bytes() : epi_smem_bytes(p.e.has_res, a.out_f32 != nullptr, a.out_bf16 != nullptr)) +
                         (anorm ? ANORM_SMEM : 0);
   const int avail = SMEM_LIMIT - SMEM_FIXED - epi_bytes;

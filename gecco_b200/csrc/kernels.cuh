@@ -36,6 +36,9 @@ int launch_lift(const gecco_lift_args& a, cudaStream_t s);
 int launch_head(const gecco_head_args& a, cudaStream_t s);
 int launch_sampler_init(const float* latents, const float* noise, double t0, double churn, long long n, double* x_hat,
                         float* xin, cudaStream_t s);
+int launch_seed_renoise(const float* data, const float* noise, float t, long long n, float* out, cudaStream_t s);
+int launch_substep_noise(const double* src, const float* n1, float c1, const float* n2, float c2, long long n, double* x_hat,
+                         float* xin, cudaStream_t s);
 int launch_lookup(const gecco_lookup_args& a, cudaStream_t s);
 int launch_fold_gn(const float* W, const float* bias, const double* stats, double count, float eps, int groups,
                    int c_in, int c_out, int clouds, void* wb, long long ldwb, float* bb, cudaStream_t s);

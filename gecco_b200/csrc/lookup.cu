@@ -36,6 +36,7 @@ struct LookupP {
   long long ldo32;
   double* stats;
   int stat_groups;
+  int glob_mask;  // staged kernel, HYBRID: bit l set = level l is NOT staged, its taps are gathered from global memory (L2)
 };
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
@@ -288,7 +289,11 @@ __device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {
 }
 
 // PACKED: blend and statistics on packed fp32x2 arithmetic (FFMA2 / FADD2) instead of scalar FFMA.
-template <int UPT, bool PACKED>
+// HYBRID: levels flagged in p.glob_mask are too large to stage (256^2 images: the 64 x 64 x 96 level is 786 KB per cloud);
+// their threads gather the four taps from the L2-resident channels-last map instead, with the taps of the NEXT point in
+// flight while the current one is blended, and the other levels still come from shared memory.  The large level is the
+// one with the FEWEST channels, so the global gather shrinks from 4 x 672 to 4 x 96 channels per point.
+template <int UPT, bool PACKED, bool HYBRID = false>
 __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const LookupP p, const int S, const int pts_per_cta) {
   extern __shared__ __align__(16) uint8_t lsm[];
   pdl_wait();  // programmatic dependent launch: the predecessor has completed
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
     nU[l] = l < p.n_levels ? p.lvl_c[l] / (8 * S) : 0;
     sm_off[l] = off;
     col_off[l] = col;
-    off += p.lvl_h[l] * p.lvl_w[l] * nU[l] * 16;
+    if (!(HYBRID && ((p.glob_mask >> l) & 1))) off += p.lvl_h[l] * p.lvl_w[l] * nU[l] * 16;
     tpp += nU[l] / UPT;
     col += p.lvl_c[l];
   }
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
 #pragma unroll
   for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
     if (nU[l] == 0) continue;
+    if (HYBRID && ((p.glob_mask >> l) & 1)) continue;  // gathered from global memory
     const int C = p.lvl_c[l], n = nU[l];
     const int total = p.lvl_h[l] * p.lvl_w[l] * n;
     const __nv_bfloat16* src = p.lvl_ptr[l] + (long long)cloud * p.lvl_h[l] * p.lvl_w[l] * C + slice * n * 8;
@@ -352,8 +358,20 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
     }
   }
   const uint8_t* gbase = lsm + my_sm + u0 * 16;
-  const int gstride = my_n * 16;
+  int gstride = my_n * 16;
   const int kstride = (my_n / UPT) * 16;  // bytes between the units of this thread
+  bool my_glob = false;
+  if constexpr (HYBRID) {
+#pragma unroll
+    for (int l = 0; l < GECCO_MAX_LEVELS; ++l) {
+      if (l == lv && ((p.glob_mask >> l) & 1)) {
+        my_glob = true;
+        const int C = p.lvl_c[l];
+        gbase = reinterpret_cast<const uint8_t*>(p.lvl_ptr[l] + (long long)cloud * p.lvl_h[l] * p.lvl_w[l] * C + slice * nU[l] * 8 + u0 * 8);
+        gstride = C * 2;  // one pixel of the channels-last map
+      }
+    }
+  }
   my_col += u0 * 8;
   const int kcol = (my_n / UPT) * 8;
 
@@ -417,6 +435,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
         ix_n = my_idx[pl];
         w4_n = my_w[pl];
       }
+      [[maybe_unused]] uint4 qn[4][UPT];
       for (int i = pl; i < cn; i += lanes) {
         const uint2 ix = ix_n;
         const float4 w4 = w4_n;
@@ -427,10 +446,31 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
         const uint32_t px[4] = {ix.x & 0xffffu, ix.x >> 16, ix.y & 0xffffu, ix.y >> 16};
         const float wt[4] = {w4.x, w4.y, w4.z, w4.w};
         uint4 q[4][UPT];
+        if (HYBRID && my_glob) {
+          // global (L2) gather, software pipelined: this point's taps were requested one iteration ago
+          if (i == pl) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+            for (int t = 0; t < 4; ++t)
 #pragma unroll
-          for (int k = 0; k < UPT; ++k) q[t][k] = *reinterpret_cast<const uint4*>(gbase + px[t] * gstride + k * kstride);
+              for (int k = 0; k < UPT; ++k) qn[t][k] = __ldg(reinterpret_cast<const uint4*>(gbase + (size_t)px[t] * gstride + k * kstride));
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) q[t][k] = qn[t][k];
+          if (i + lanes < cn) {
+            const uint32_t pn[4] = {ix_n.x & 0xffffu, ix_n.x >> 16, ix_n.y & 0xffffu, ix_n.y >> 16};
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+              for (int k = 0; k < UPT; ++k) qn[t][k] = __ldg(reinterpret_cast<const uint4*>(gbase + (size_t)pn[t] * gstride + k * kstride));
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) q[t][k] = *reinterpret_cast<const uint4*>(gbase + px[t] * gstride + k * kstride);
+        }
         __nv_bfloat16* orow = p.out16 + ((long long)cloud * p.rows_per_cloud + c0 + i) * p.ldo16 + my_col;
 #pragma unroll
         for (int k = 0; k < UPT; ++k) {
@@ -529,9 +569,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lookup_staged_kernel(const Look
 struct StagedPlan {
   int S, upt;
   size_t smem;
+  int glob_mask;  // levels left in global memory (hybrid kernel)
 };
 StagedPlan plan_staged(const LookupP& p, int stat_groups) {
-  StagedPlan none = {0, 0, 0};
+  StagedPlan none = {0, 0, 0, 0};
   if (p.out16 == nullptr || p.out32 != nullptr) return none;
   if (stat_groups > 64) return none;
   int forced = -1;
@@ -542,8 +583,17 @@ StagedPlan plan_staged(const LookupP& p, int stat_groups) {
   // Measured at 64 clouds x 2048 points (tools/lookup_time.py): 137^2 pyramids (S = 2) 105 us against 228 us for the
   // global-gather kernel; 256^2 pyramids need S = 12 (7 threads per point, a tap-table entry per 8 channels) and are
   // slower than the global gather (270 against 236 us), so the automatic choice stops at S = 4.
+  // Hybrid plans (GECCO_LOOKUP_HYBRID=0 disables them): first everything staged; if no S <= 4 fits, the level with the
+  // largest map (the fewest channels in a CNN pyramid) stays in global memory and only the others are staged.
+  const char* hv = getenv("GECCO_LOOKUP_HYBRID");
+  const bool hybrid_ok = !(hv != nullptr && hv[0] == '0') && p.n_levels >= 2;
+  int biggest = 0;
+  for (int l = 1; l < p.n_levels; ++l)
+    if ((size_t)p.lvl_h[l] * p.lvl_w[l] * p.lvl_c[l] > (size_t)p.lvl_h[biggest] * p.lvl_w[biggest] * p.lvl_c[biggest]) biggest = l;
   static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48};
+  for (int pass = 0; pass < (hybrid_ok && forced < 0 ? 2 : 1); ++pass)
   for (int S : cand) {
+    const int glob_mask = pass == 1 ? (1 << biggest) : 0;
     if (forced > 0 && S != forced) continue;
     if (forced < 0 && S > 4) break;
     bool ok = true, even = true;
@@ -554,7 +604,7 @@ StagedPlan plan_staged(const LookupP& p, int stat_groups) {
       const int n = p.lvl_c[l] / (8 * S);
       even = even && (n % 2 == 0);
       units += n;
-      bytes += (size_t)p.lvl_h[l] * p.lvl_w[l] * n * 16;
+      if (!((glob_mask >> l) & 1)) bytes += (size_t)p.lvl_h[l] * p.lvl_w[l] * n * 16;
     }
     if (!ok) continue;
     const int upt = even ? 2 : 1;
@@ -566,7 +616,7 @@ StagedPlan plan_staged(const LookupP& p, int stat_groups) {
     if (red > total) total = red;
     total += LS_SGRP_BYTES;
     if (total > LS_SMEM_MAX) continue;
-    return {S, upt, total};
+    return {S, upt, total, glob_mask};
   }
   return none;
 }
@@ -665,8 +715,10 @@ int launch_lookup(const gecco_lookup_args& a, cudaStream_t s) {
   p.stats = a.stats; p.stat_groups = a.stats ? a.stat_groups : 0;
   if (a.points == 0 || a.clouds == 0) return GECCO_OK;
   GECCO_REQUIRE(!a.stats || ctot / a.stat_groups >= 8, "lookup: GroupNorm groups must be at least 8 channels wide");
+  p.glob_mask = 0;
   const StagedPlan plan = plan_staged(p, p.stat_groups);
   if (plan.S > 0) {
+    p.glob_mask = plan.glob_mask;
     // (slice, cloud, point range): point ranges only when clouds x slices leave SMs idle
     int z = sm_count() / (a.clouds * plan.S);
     if (z < 1) z = 1;
@@ -682,8 +734,10 @@ int launch_lookup(const gecco_lookup_args& a, cudaStream_t s) {
       }
       launch_pdl(kern, grid, dim3(LS_THREADS), plan.smem, s, p, plan.S, per);
     };
-    static bool attr_done[4] = {false, false, false, false};
-    if (plan.upt == 2 && packed) go(lookup_staged_kernel<2, true>, attr_done[0]);
+    static bool attr_done[6] = {false, false, false, false, false, false};
+    if (plan.glob_mask != 0 && plan.upt == 2) go(lookup_staged_kernel<2, true, true>, attr_done[4]);
+    else if (plan.glob_mask != 0) go(lookup_staged_kernel<1, true, true>, attr_done[5]);
+    else if (plan.upt == 2 && packed) go(lookup_staged_kernel<2, true>, attr_done[0]);
     else if (plan.upt == 2) go(lookup_staged_kernel<2, false>, attr_done[1]);
     else if (packed) go(lookup_staged_kernel<1, true>, attr_done[2]);
     else go(lookup_staged_kernel<1, false>, attr_done[3]);

@@ -204,6 +204,71 @@ class Diffusion(_Base):
                        K=None if context is None else context.K)
         return self.reparam.diffusion_to_data(x, context)
 
+    @torch.no_grad()
+    def sample_ode(self, shape: Sequence[int], context: Context3d | None, rng: torch.Generator = None, **kwargs) -> Tensor:
+        """Deterministic sampler: Heun's method on the probability-flow ODE dx/dt = (x - D(x; t)) / t over the EDM noise
+        levels (gecco-jax `solve_sample_ode`, models/diffusion.py:334-374, with the sigma(t) = t schedule of gecco-torch).
+        It is the stochastic sampler with S_churn = 0, run by the same `gecco_sample` loop; only the latents are drawn."""
+        kw = {**self.sampler_kwargs, **kwargs, "S_churn": 0.0}
+        num_steps = kw["num_steps"]
+        device, dtype = self.example_param.device, self.example_param.dtype
+        if rng is None:
+            rng = torch.Generator(device).manual_seed(42)
+        latents = self._randn(shape, rng, device, dtype)
+        post_context = self.conditioner(context)
+        ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])
+        net, sigma_data = self._network()
+        eng = engine_for(net, sigma_data)
+        _, noise = eng.sample_buffers(latents.shape[0], latents.shape[1], num_steps, device)  # never read: all gammas are 0
+        x = eng.sample(latents, noise, ts.tolist(), [0.0] * num_steps, kw["S_noise"], post_context=post_context,
+                       K=None if context is None else context.K)
+        return self.reparam.diffusion_to_data(x, context)
+
+    @torch.no_grad()
+    def sample_inpaint(self, known: Tensor, m_to_inpaint: int, context: Context3d | None, rng: torch.Generator = None,
+                       num_substeps: int = 1, **kwargs) -> Tensor:
+        """Completion of a partial cloud (gecco-jax `sample_inpaint`, models/stochastic.py:101-231): `m_to_inpaint` new
+        points are sampled jointly with the `known` points [B, N, 3] (data space), which are re-imposed at the current
+        noise level before every sub-step; returns the float64 [B, m_to_inpaint, 3] completions.  Draw order per
+        sub-step: known-point noise, churn noise, re-noise (the last only between sub-steps).  Every evaluation runs in
+        the engine with the Euler / Heun update fused into its head kernel (gecco_denoise modes 2 / 3)."""
+        kw = {**self.sampler_kwargs, "S_churn": 0.0, **kwargs}  # the JAX sampler defaults to s_churn = 0
+        num_steps, S_churn, S_noise = kw["num_steps"], kw["S_churn"], kw["S_noise"]
+        device, dtype = self.example_param.device, self.example_param.dtype
+        if rng is None:
+            rng = torch.Generator(device).manual_seed(42)
+        randn = lambda shape: self._randn(shape, rng, device, dtype)
+        known_diff = self.reparam.data_to_diffusion(known.to(device), context).to(dtype)
+        B, N = known_diff.shape[0], known_diff.shape[1]
+        M = int(m_to_inpaint)
+        post_context = self.conditioner(context)
+        K = None if context is None else context.K
+        ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"]).tolist()
+        gamma = min(S_churn / num_steps, math.sqrt(2.0) - 1)
+        net, sigma_data = self._network()
+        eng = engine_for(net, sigma_data)
+        x = torch.cat([torch.zeros(B, M, 3, device=device, dtype=dtype), known_diff], dim=1).to(torch.float64)
+        x = x + (randn(x.shape) * ts[0]).to(torch.float64)
+        x_hat = torch.empty_like(x)
+        x_next, d_cur = torch.empty_like(x), torch.empty_like(x)
+        xin_a, xin_b = torch.empty(x.shape, device=device, dtype=torch.float32), torch.empty(x.shape, device=device, dtype=torch.float32)
+        for i in range(num_steps):
+            s_cur, s_next = ts[i], ts[i + 1]
+            s_hat = s_cur * (1 + gamma)
+            for j in range(num_substeps):
+                x[:, M:] = (known_diff + randn(known_diff.shape) * s_cur).to(torch.float64)
+                x_hat.copy_(x + (math.sqrt(s_hat**2 - s_cur**2) * S_noise * randn(x.shape)).to(torch.float64))
+                xin_a.copy_(x_hat)
+                eng.sampler_eval(xin_a, s_hat, 2, x_hat, x_next, d_cur, xin_b, s_hat, s_next, post_context, K)
+                if i < num_steps - 1:
+                    eng.sampler_eval(xin_b, s_next, 3, x_hat, x_next, d_cur, xin_a, s_hat, s_next, post_context, K)
+                    x.copy_(x_hat)
+                else:
+                    x.copy_(x_next)
+                if j < num_substeps - 1:
+                    x += (math.sqrt(max(s_cur**2 - s_next**2, 0.0)) * randn(x.shape)).to(torch.float64)
+        return self.reparam.diffusion_to_data(x, context)[:, :M]
+
     def _network(self):
         bb = self.backbone
         if not isinstance(bb, EDMPrecond):
@@ -234,31 +299,15 @@ class Diffusion(_Base):
         ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])
         gammas = self._gammas(ts, num_steps, S_churn, S_min, S_max)
         net, sigma_data = self._network()
-        eng = engine_for(net, sigma_data)
-        K = None if context is None else context.K
-        B = data.shape[0]
-        tl = ts.tolist()
-        x_next = new_latents.to(torch.float64) * tl[0]
-        for i in range(num_steps):
-            t_cur, t_next = tl[i], tl[i + 1]
-            data_ctx = data + randn(data.shape) * t_cur
-            sig = torch.full((B,), t_cur, device=device, dtype=torch.float64).to(dtype)
-            _, cache = eng.denoise(data_ctx.to(dtype), sig, post_context=post_context, K=K, do_cache=True)
-            for u in range(num_substeps):
-                x_cur = x_next
-                t_hat = t_cur + gammas[i] * t_cur
-                churn = torch.tensor(math.sqrt(t_hat**2 - t_cur**2) * S_noise, dtype=dtype, device=device)
-                x_hat = x_cur + churn * randn(x_cur.shape)
-                sig = torch.full((B,), t_hat, device=device, dtype=torch.float64).to(dtype)
-                den, _ = eng.denoise(x_hat.to(dtype), sig, post_context=post_context, K=K, cache=cache)
-                d_cur = (x_hat - den.to(torch.float64)) / t_hat
-                x_next = x_hat + (t_next - t_hat) * d_cur
-                if i < num_steps - 1:
-                    sig = torch.full((B,), t_next, device=device, dtype=torch.float64).to(dtype)
-                    den, _ = eng.denoise(x_next.to(dtype), sig, post_context=post_context, K=K, cache=cache)
-                    d_prime = (x_next - den.to(torch.float64)) / t_next
-                    x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
-                if u < num_substeps - 1 and i < num_steps - 1:
-                    redo = torch.tensor(math.sqrt(t_cur**2 - t_next**2), dtype=dtype, device=device)
-                    x_next = x_next + redo * randn(x_next.shape)
+
+        def draw(out: Tensor):  # one `randn(shape)` of the reference, written in place (tests/test_engine_state_gpu.py)
+            if rng.device == out.device:
+                out.normal_(generator=rng)
+            else:
+                out.copy_(self._randn(out.shape, rng, device, out.dtype))
+
+        # the whole loop runs in the engine: one gecco_upsample_step per noise level (seed re-noising, full evaluation
+        # with cached inducer states, num_substeps x {churn, cached Euler / Heun evaluations, re-noise})
+        x_next = engine_for(net, sigma_data).upsample(data.to(dtype), new_latents, ts.tolist(), gammas, S_noise, num_substeps, draw,
+                                                      post_context=post_context, K=None if context is None else context.K)
         return self.reparam.diffusion_to_data(x_next, context)

@@ -294,11 +294,12 @@ class Engine:
         """Persistent (latents [B,N,3], noise [steps,B,N,3]) fp32 input buffers of `sample`.  Drawing the noise straight
         into them saves a copy and, because their addresses never change, lets `gecco_sample` replay its captured CUDA
         graph instead of re-enqueueing ~12 000 launches per call."""
-        key = (B, N, steps, str(device))
+        key = ("smp", B, N, steps, str(device))
         io = self._io.get(key)
         if io is None:
-            if len(self._io) >= 2:  # bounded: a new shape evicts the oldest buffers
-                self._io.pop(next(iter(self._io)))
+            old = [k for k in self._io if k[0] == "smp"]
+            if len(old) >= 2:  # bounded: a new shape evicts the oldest buffers
+                self._io.pop(old[0])
             io = dict(lat=torch.empty((B, N, 3), device=device, dtype=torch.float32),
                       noise=torch.empty((steps, B, N, 3), device=device, dtype=torch.float32),
                       out=torch.empty((B, N, 3), device=device, dtype=torch.float64))
@@ -334,7 +335,7 @@ class Engine:
         a.latents, a.noise = lat.data_ptr(), nz.data_ptr()
         ctx, keep = self._context(post_context, K, B)
         a.ctx = ctx
-        out = self._io[(B, N, steps, str(latents.device))]["out"]
+        out = self._io[("smp", B, N, steps, str(latents.device))]["out"]
         a.x_out = out.data_ptr()
         ws = self._workspace(B, N, latents.device)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -343,6 +344,89 @@ class Engine:
             _abi.check(self._lib.gecco_sample(self._handle, C.byref(a), stream))
         del keep
         return out.clone()  # the caller owns the result; the persistent buffer is overwritten by the next call
+
+
+    @torch.no_grad()
+    def sampler_eval(self, xin: Tensor, sigma: float, mode: int, x_hat: Tensor, x_next: Tensor, d_cur: Tensor, xin_next: Tensor,
+                     t_hat: float, t_next: float, post_context=None, K: Optional[Tensor] = None) -> None:
+        """One evaluation whose head applies a sampler update in place on float64 state (gecco_denoise modes 2 / 3):
+        mode 2 Euler (d_cur, x_next from x_hat), mode 3 Heun (x_hat <- corrected point).  `xin_next` receives the fp32
+        copy of the new point.  Building block of samplers with host-side control flow (e.g. sample_inpaint)."""
+        self._ensure(xin.device)
+        B, N = xin.shape[0], xin.shape[1]
+        for t_, dt in ((xin, torch.float32), (x_hat, torch.float64), (x_next, torch.float64), (d_cur, torch.float64), (xin_next, torch.float32)):
+            if t_.dtype != dt or not t_.is_contiguous() or tuple(t_.shape) != (B, N, 3):
+                raise ValueError("gecco_b200: sampler state tensors must be contiguous [B, N, 3] (float32 inputs, float64 state)")
+        a = _abi.DenoiseArgs()
+        a.x, a.sigma_imm = xin.data_ptr(), float(sigma)
+        a.clouds, a.points = B, N
+        ctx, keep = self._context(post_context, K, B)
+        a.ctx = ctx
+        a.mode = mode
+        a.x_hat, a.x_next, a.d_cur, a.xin_next = x_hat.data_ptr(), x_next.data_ptr(), d_cur.data_ptr(), xin_next.data_ptr()
+        a.t_hat, a.t_next = float(t_hat), float(t_next)
+        ws = self._workspace(B, N, xin.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(xin.device):
+            stream = C.c_void_p(torch.cuda.current_stream(xin.device).cuda_stream)
+            _abi.check(self._lib.gecco_denoise(self._handle, C.byref(a), stream))
+        del keep
+
+    @torch.no_grad()
+    def upsample(self, data_diffusion: Tensor, new_latents: Tensor, t_steps: Sequence[float], gammas: Sequence[float],
+                 s_noise: float, num_substeps: int, draw, post_context=None, K: Optional[Tensor] = None) -> Tensor:
+        """The loop of Diffusion.upsample (diffusion.py:421-466): one `gecco_upsample_step` per noise level.
+        `draw(out)` fills a float32 tensor with the next standard-normal draw of the caller's generator (the draws are
+        made in the reference order: seed re-noising, then per sub-step churn and re-noise).  data_diffusion
+        [B, Ns, 3] is the seed cloud in diffusion space, new_latents [B, Nn, 3]; returns the float64 diffusion-space
+        result [B, Nn, 3]."""
+        if not data_diffusion.is_cuda:
+            raise _abi.GeccoError("gecco_b200 needs CUDA tensors (there is no CPU path)")
+        dev = data_diffusion.device
+        self._ensure(dev)
+        B, Ns, Nn = data_diffusion.shape[0], data_diffusion.shape[1], new_latents.shape[1]
+        steps = len(gammas)
+        assert len(t_steps) == steps + 1
+        # persistent buffers (stable addresses): a repeated call with the same shapes and schedule replays the 64 captured
+        # per-noise-level graphs instead of re-enqueueing ~40 000 launches
+        ukey = ("ups", B, Ns, Nn, num_substeps, str(dev))
+        io = self._io.get(ukey)
+        if io is None:
+            for k in [k for k in self._io if k[0] == "ups"]:
+                self._io.pop(k)
+            io = dict(seed=torch.empty((B, Ns, 3), device=dev, dtype=torch.float32),
+                      seed_noise=torch.empty((B, Ns, 3), device=dev, dtype=torch.float32),
+                      noise=torch.empty((2 * num_substeps - 1, B, Nn, 3), device=dev, dtype=torch.float32),
+                      x=torch.empty((B, Nn, 3), device=dev, dtype=torch.float64))
+            self._io[ukey] = io
+        seed, seed_noise, noise, x = io["seed"], io["seed_noise"], io["noise"], io["x"]
+        seed.copy_(data_diffusion.detach())
+        torch.mul(new_latents.detach().to(torch.float64), float(t_steps[0]), out=x)
+        ctx, keep = self._context(post_context, K, B)
+        need = int(self._lib.gecco_upsample_workspace_bytes(self._handle, B, Ns, Nn))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+        a = _abi.UpsampleStepArgs()
+        a.clouds, a.seed_points, a.new_points, a.num_substeps = B, Ns, Nn, num_substeps
+        a.s_noise = float(s_noise)
+        a.seed_data, a.seed_noise, a.noise, a.x = seed.data_ptr(), seed_noise.data_ptr(), noise.data_ptr(), x.data_ptr()
+        a.ctx = ctx
+        a.workspace, a.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        with torch.cuda.device(dev):
+            for i in range(steps):
+                last = i == steps - 1
+                draw(seed_noise)
+                for u in range(num_substeps):
+                    draw(noise[u if last else 2 * u])
+                    if u < num_substeps - 1 and not last:
+                        draw(noise[2 * u + 1])
+                a.last_step = 1 if last else 0
+                a.t_cur, a.t_next, a.gamma = float(t_steps[i]), float(t_steps[i + 1]), float(gammas[i])
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                _abi.check(self._lib.gecco_upsample_step(self._handle, C.byref(a), stream))
+        del keep
+        return x.clone()
 
 
 _ENGINES: "weakref.WeakKeyDictionary[torch.nn.Module, dict]" = weakref.WeakKeyDictionary()

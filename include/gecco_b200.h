@@ -406,6 +406,27 @@ int gecco_sample(gecco_engine* e, const gecco_sample_args* args, void* stream);
  * call ran eagerly.  A graph is reused only when every argument (shapes, schedule, all pointers) is identical. */
 int gecco_graph_status(const gecco_engine* e);
 
+/* One step of Diffusion.upsample (diffusion.py:427-466): re-noise the seed cloud to t_cur, one full evaluation on it that
+ * caches the inducer states, then num_substeps x { churn, cached Euler evaluation, cached Heun evaluation (unless
+ * last_step), re-noise (unless the last sub-step or last_step) } on the new points, with the preconditioning and the
+ * Euler / Heun arithmetic fused into the head kernel of each cached evaluation and float64 sampler state.
+ *   seed_data  [clouds, seed_points, 3] fp32  diffusion-space seed cloud (reparam.data_to_diffusion of the input)
+ *   seed_noise [clouds, seed_points, 3] fp32  the step's `randn(data.shape)`
+ *   noise      fp32 draws on the new points in the reference order: churn_0, redo_0, churn_1, ..., churn_{S-1}
+ *              ([2S-1][clouds, new_points, 3]; last_step: churn_0 .. churn_{S-1}, [S][...])
+ *   x          float64 [clouds, new_points, 3]: x_next of the previous step in, x_next of this step out.
+ * t_hat = t_cur + gamma t_cur; churn = sqrt(t_hat^2 - t_cur^2) s_noise; redo = sqrt(t_cur^2 - t_next^2). */
+typedef struct gecco_upsample_step_args {
+  int32_t clouds, seed_points, new_points, num_substeps, last_step;
+  double t_cur, t_next, gamma, s_noise;
+  const float* seed_data; const float* seed_noise; const float* noise;
+  double* x;
+  gecco_context ctx;
+  void* workspace; int64_t workspace_bytes;
+} gecco_upsample_step_args;
+int64_t gecco_upsample_workspace_bytes(const gecco_engine* e, int32_t clouds, int32_t seed_points, int32_t new_points);
+int gecco_upsample_step(gecco_engine* e, const gecco_upsample_step_args* args, void* stream);
+
 /* Per-kernel-class device timing of the engine (tracing aid; the reference has none).  Between
  * start and stop every engine launch on this thread is bracketed by CUDA events on its stream; stop synchronises
  * the device and returns, per class, the launch count, summed device time and the algorithmic FLOPs / bytes. */

@@ -311,6 +311,43 @@ def upsample(cfg: OracleConfig, sd: dict, data: Tensor, n_new: int | None = None
     return diffusion_to_data(cfg, sd, x_next, K)
 
 
+# gecco-jax models/stochastic.py:101-231 (`_sample_inpaint`), restated with the EDM schedule sigma(t) = t of gecco-torch and
+# torch draws in the order: initial noise; per sub-step known-point noise, churn noise, re-noise.  gecco-jax cannot run in
+# the build container (no jax / equinox / diffrax), so this restatement is NOT pinned by reference outputs.
+@torch.no_grad()
+def sample_inpaint(cfg: OracleConfig, sd: dict, known: Tensor, m_to_inpaint: int, features=None, K=None,
+                   rng: torch.Generator | None = None, num_substeps: int = 1, **kw):
+    k = {**cfg.sampler, "sigma_max": cfg.sigma_max, "S_churn": 0.0, **kw}
+    n, S_churn, S_noise = k["num_steps"], k["S_churn"], k["S_noise"]
+    if rng is None:
+        rng = torch.Generator("cpu").manual_seed(42)
+    randn = lambda shape: torch.randn(tuple(shape), generator=rng, dtype=torch.float32)
+    known_diff = data_to_diffusion(cfg, sd, known, K).float()
+    B, N = known_diff.shape[:2]
+    M = m_to_inpaint
+    ts = t_steps(n, k["sigma_max"], k["sigma_min"], k["rho"]).tolist()
+    gamma = min(S_churn / n, math.sqrt(2.0) - 1)
+    x = torch.cat([torch.zeros(B, M, 3), known_diff], dim=1).to(torch.float64)
+    x = x + (randn(x.shape) * ts[0]).to(torch.float64)
+    for i in range(n):
+        s_cur, s_next = ts[i], ts[i + 1]
+        s_hat = s_cur * (1 + gamma)
+        for j in range(num_substeps):
+            x[:, M:] = (known_diff + randn(known_diff.shape) * s_cur).to(torch.float64)
+            x_hat = x + (math.sqrt(s_hat**2 - s_cur**2) * S_noise * randn(x.shape)).to(torch.float64)
+            sig = torch.full((B,), s_hat, dtype=torch.float32)
+            d_cur = (x_hat - denoise(cfg, sd, x_hat.float(), sig, features, K).to(torch.float64)) / s_hat
+            x_next = x_hat + (s_next - s_hat) * d_cur
+            if i < n - 1:
+                sig = torch.full((B,), s_next, dtype=torch.float32)
+                d_prime = (x_next - denoise(cfg, sd, x_next.float(), sig, features, K).to(torch.float64)) / s_next
+                x_next = x_hat + (s_next - s_hat) * (0.5 * d_cur + 0.5 * d_prime)
+            x = x_next
+            if j < num_substeps - 1:
+                x = x + (math.sqrt(max(s_cur**2 - s_next**2, 0.0)) * randn(x.shape)).to(torch.float64)
+    return diffusion_to_data(cfg, sd, x, K)[:, :M]
+
+
 # diffusion.py:87-143 — LogUniformSchedule (low-discrepancy) + EDMLoss on given draws u ~ U[0,1)^B, noise ~ N(0,1)
 def edm_loss(cfg: OracleConfig, sd: dict, examples: Tensor, u: Tensor, noise: Tensor, features=None, K=None,
              sigma_min: float = 0.002, loss_scale: float = 100.0) -> Tensor:

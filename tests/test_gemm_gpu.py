@@ -186,9 +186,10 @@ def test_gemm_pair_percloud_act(cuda, pairs):
         assert o16[b * Np + N:(b + 1) * Np].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("src", ["bf16"])
 @pytest.mark.parametrize("n_out,act", [(1152, None), (768, 1.3), (384, None)])
 @pytest.mark.parametrize("clouds,rows_per_cloud,valid", [(3, 768, 700), (16, 2048, 2048)])
-def test_gemm_anorm_operand(cuda, n_out, act, clouds, rows_per_cloud, valid):
+def test_gemm_anorm_operand(cuda, n_out, act, clouds, rows_per_cloud, valid, src):
     """AdaGN applied to the A operand inside the CTA-pair GEMM (gecco_anorm): bf16 x -> a * x + s in fp32 -> bf16, in place
     in shared memory -> tcgen05, against AdaGN in torch (models/normalization.py:36-44) of the same bf16 x followed by
     the same bf16 projection."""
@@ -200,9 +201,10 @@ def test_gemm_anorm_operand(cuda, n_out, act, clouds, rows_per_cloud, valid):
     m = clouds * rows_per_cloud
     assert ops.gemm_anorm_supported(m, rows_per_cloud, n_out, K)
     g = torch.Generator(device="cpu").manual_seed(n_out + clouds)
-    x = (torch.randn(clouds, rows_per_cloud, K, generator=g) * 0.7 + torch.randn(1, 1, K, generator=g) * 1.5).to(cuda)
+    x = (torch.randn(clouds, rows_per_cloud, K, generator=g) * 0.7 + torch.randn(1, 1, K, generator=g) * (1.5 if src == "bf16" else 6.0)).to(cuda)
     x[:, valid:] = 0.0  # padding rows of the residual stream are zeros
-    x = x.bfloat16().float()  # the operand the kernel reads is the bf16 copy of the residual stream
+    if src == "bf16":
+        x = x.bfloat16().float()  # the operand the kernel reads is the bf16 copy of the residual stream
     x2 = x.view(m, K)
     w = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
     bias = torch.randn(n_out, generator=g).to(cuda)
@@ -210,8 +212,9 @@ def test_gemm_anorm_operand(cuda, n_out, act, clouds, rows_per_cloud, valid):
     sw, sb = (torch.randn(K, 1, generator=g) * 0.3).to(cuda), (torch.randn(K, generator=g) * 0.1 + 1).to(cuda)
     bw, bb = (torch.randn(K, 1, generator=g) * 0.3).to(cuda), (torch.randn(K, generator=g) * 0.1).to(cuda)
     stats = ops.group_stats(x2, rows_per_cloud, valid, 12)
-    _, o16 = ops.gemm(x2.bfloat16(), w, bias=bias, act_alpha=act, out_bf16=True, rows_per_cloud=rows_per_cloud, valid_rows=valid,
-                      anorm=dict(stats=stats, t=t, scale_w=sw, scale_b=sb, bias_w=bw, bias_b=bb, groups=groups))
+    extra = dict(x=x2) if src == "fp32" else {}
+    _, o16 = ops.gemm(None if src == "fp32" else x2.bfloat16(), w, bias=bias, act_alpha=act, out_bf16=True, rows_per_cloud=rows_per_cloud,
+                      valid_rows=valid, anorm=dict(stats=stats, **extra, t=t, scale_w=sw, scale_b=sb, bias_w=bw, bias_b=bb, groups=groups))
     torch.cuda.synchronize()
     xv = x[:, :valid]
     normed = F.group_norm(xv.transpose(1, 2), groups, eps=1e-5).transpose(1, 2)

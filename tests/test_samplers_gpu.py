@@ -1,0 +1,64 @@
+"""The samplers gecco-torch lists as missing and gecco-jax has: deterministic probability-flow ODE
+sampling (Heun) and inpainting, both on the engine, against the CPU oracle on tame weights (contractive map) with the same
+CPU-generator draws.  gecco-jax cannot be imported in the build container, so these are pinned to the oracle's restatement
+(oracle/gecco_oracle.py: sample_stochastic with S_churn = 0, sample_inpaint), not to reference outputs."""
+import pytest
+import torch
+
+from oracle import gecco_oracle as O
+from tests import synth
+from tests.models_b200 import build
+
+pytestmark = pytest.mark.gpu
+
+
+def rms(t):
+    return t.double().pow(2).mean().sqrt().item()
+
+
+def _model(cuda, kind, feats=None):
+    rp = synth.SHAPENET_VOL_REPARAM if kind == "cond" else synth.UNCOND_REPARAM
+    sd = synth.tame(synth.full_state_dict(kind, "gaussian", rp["mean"], rp["sigma"], 1234), 0.15)
+    model = build(kind, "gaussian", rp["mean"], rp["sigma"], 165.0, None, cuda, feats, state_dict=sd)
+    return model, sd, rp
+
+
+def test_ode_sampler_matches_oracle(cuda):
+    import gecco_b200 as G
+
+    B, N, steps = 2, 384, 12
+    feats = synth.synth_features(B, (34, 17, 8), 21)
+    model, sd, rp = _model(cuda, "cond", feats)
+    K = synth.camera(B, synth.K_SHAPENET)
+    ctx = G.Context3d(image=torch.zeros(B, 3, 8, 8, device=cuda), K=K.to(cuda))
+    cfg = O.OracleConfig(kind="cond", reparam="gaussian", sigma_max=165.0)
+    got = model.sample_ode((B, N, 3), ctx, rng=synth.gen(3), num_steps=steps)
+    ref = O.sample_stochastic(cfg, sd, (B, N, 3), feats, K, rng=synth.gen(3), num_steps=steps, S_churn=0.0)
+    to_diff = lambda d: O.data_to_diffusion(cfg, sd, d.cpu().double(), None)
+    e = rms(to_diff(got) - to_diff(ref)) / rms(to_diff(ref))
+    print("ODE sampler rel rms (diffusion space)", e)
+    assert got.dtype == torch.float64 and e < 1e-2
+    # deterministic: the same latents give the same cloud, bit for bit, and no noise is consumed from the generator
+    g = synth.gen(3)
+    again = model.sample_ode((B, N, 3), ctx, rng=g, num_steps=steps)
+    assert torch.equal(got, again)
+    assert torch.equal(torch.randn(4, generator=g), torch.randn(4, generator=_after_latents(3, (B, N, 3))))
+
+
+def _after_latents(seed, shape):
+    g = synth.gen(seed)
+    torch.randn(shape, generator=g)
+    return g
+
+
+def test_inpaint_matches_oracle(cuda):
+    B, N, M, steps = 2, 200, 184, 6
+    model, sd, rp = _model(cuda, "uncond")
+    cfg = O.OracleConfig(kind="uncond", reparam="gaussian", sigma_max=165.0)
+    known = O.diffusion_to_data(cfg, sd, torch.randn(B, N, 3, generator=synth.gen(5)), None)
+    got = model.sample_inpaint(known.to(cuda), M, None, rng=synth.gen(6), num_substeps=2, num_steps=steps, S_churn=0.5)
+    ref = O.sample_inpaint(cfg, sd, known, M, rng=synth.gen(6), num_substeps=2, num_steps=steps, S_churn=0.5)
+    to_diff = lambda d: O.data_to_diffusion(cfg, sd, d.cpu().double(), None)
+    e = rms(to_diff(got) - to_diff(ref)) / rms(to_diff(ref))
+    print("inpaint rel rms (diffusion space)", e)
+    assert got.shape == (B, M, 3) and got.dtype == torch.float64 and e < 1e-2

@@ -31,6 +31,8 @@ for label, n_out, percloud, act, res, anorm in CASES:
         continue
     w = (torch.randn((B if percloud else 1) * n_out, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
     bias = torch.randn(B if percloud else 1, n_out, generator=g).to(dev)
+    if not percloud:
+        bias = bias[0].contiguous()
     out = torch.empty(B * Np, n_out, device=dev, dtype=torch.bfloat16)
     x = torch.randn(B * Np, n_out, device=dev) if res else None
     dbg = torch.zeros(148, 32, dtype=torch.int64, device=dev)

@@ -14,12 +14,14 @@ import bench  # noqa: E402
 import gecco_b200 as G  # noqa: E402
 
 
-def main(evals: int = 2, clouds: int = bench.CLOUDS_PER_GPU):
+def main(evals: int = 2, config: int = 2):
     dev = torch.device("cuda:0")
-    model = bench.build_model(dev)
+    cfg = bench.CONFIGS[config]
+    clouds = cfg["clouds"]
+    model = bench.build_model(dev, cfg)
     g = torch.Generator("cpu").manual_seed(123)
-    ctx = G.Context3d(image=torch.rand(clouds, 3, bench.IMAGE, bench.IMAGE, generator=g).to(dev),
-                      K=torch.tensor(bench.K_CAM).expand(clouds, 3, 3).contiguous().to(dev))
+    ctx = G.Context3d(image=torch.rand(clouds, 3, cfg["image"], cfg["image"], generator=g).to(dev),
+                      K=torch.tensor(cfg["K"]).expand(clouds, 3, 3).contiguous().to(dev))
     post = model.conditioner(ctx)
     x = torch.randn(clouds, bench.POINTS, 3, generator=g).to(dev)
     sigma = torch.full((clouds,), 1.5, device=dev)
@@ -30,4 +32,4 @@ def main(evals: int = 2, clouds: int = bench.CLOUDS_PER_GPU):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 2)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 2, int(sys.argv[2]) if len(sys.argv) > 2 else 2)
