@@ -398,7 +398,15 @@ __device__ __forceinline__ void epi_panel(const EpiParams& p, const EpiSmem& sm,
 // compile-time, the three chunks of a warp are drained from TMEM back to back (three tcgen05.ld in flight) and the
 // accumulator slot is handed back to the MMA issuer BEFORE the conversion and the stores; the three 32 x 32 bf16 blocks
 // go through three staging areas per warp and leave with one fence and one bulk group.
-constexpr int EPI_FAST_O16_BYTES = 3 * EPI_O16_BYTES;  // per group: 4 warps x 3 chunks x 2 KB
+// Staging areas per warp (2 KB each).  3: one fence and one bulk group per tile; 1: the three blocks go out one after the
+// other through the same area (wait for the previous store to have read it).  The epilogue warps idle more than half of
+// the time behind the MMA issuer once the accumulator is released early, so the single area is the default: the 32 KB it
+// frees go to the weight ring, which is what the issuer actually waits for.
+#ifndef GECCO_EPI_FAST_BUFS
+#define GECCO_EPI_FAST_BUFS 1
+#endif
+constexpr int EPI_FAST_BUFS = GECCO_EPI_FAST_BUFS;
+constexpr int EPI_FAST_O16_BYTES = EPI_FAST_BUFS * EPI_O16_BYTES;  // per group: 4 warps x EPI_FAST_BUFS x 2 KB
 
 __host__ __device__ inline int epi_fast_smem_bytes() { return EPI_GROUPS * EPI_FAST_O16_BYTES + EPI_BIAS_BYTES; }
 
@@ -409,16 +417,18 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, const EpiThrea
   const uint32_t ta = taddr + t.grp * EPI_CHUNK;
 #pragma unroll
   for (int k = 0; k < 3; ++k) tmem_ld32_issue(ta + 2 * k * EPI_CHUNK, rr[k]);
-  // the previous tile's bulk stores have finished reading the staging areas (issued a whole tile ago)
-  if (t.lane == 0) tma_store_wait_read<0>();
-  uint32_t pk[3][EPI_CHUNK / 2];
+  const bool zero_row = p.valid_rows < p.rows_per_cloud && !row_valid;  // padding rows are written as exact zeros
+  const uint32_t wst = stage_base + (uint32_t)(t.grp * 4 + t.q) * (EPI_FAST_BUFS * 2048u);  // this warp: 32 rows x 64 B, 64 B swizzle
+  if (EPI_FAST_BUFS == 3 && t.lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have read the staging areas
+  uint32_t pk[EPI_FAST_BUFS == 3 ? 3 : 1][EPI_CHUNK / 2];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
+    uint32_t (&pw)[EPI_CHUNK / 2] = pk[EPI_FAST_BUFS == 3 ? k : 0];
     float4 b[EPI_CHUNK / 4];
 #pragma unroll
     for (int j = 0; j < EPI_CHUNK / 4; ++j) b[j] = lds128(t.bias + k * 128u + j * 16u);
     tmem_ld32_wait(rr[k]);
-    if (k == 2) release();  // all three chunks are in registers: the accumulator slot goes back to the MMA issuer
+    if (k == 0) release();  // tcgen05.wait::ld covers all three loads: the accumulator slot goes back to the MMA issuer
 #pragma unroll
     for (int j = 0; j < EPI_CHUNK / 4; ++j) {
       float v0 = __uint_as_float(rr[k][4 * j + 0]) + b[j].x, v1 = __uint_as_float(rr[k][4 * j + 1]) + b[j].y;
@@ -429,29 +439,39 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, const EpiThrea
         v2 = fmaf(ex2_approx(v2 * v2 * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
         v3 = fmaf(ex2_approx(v3 * v3 * p.act_k), 1.0f / 0.28f, -0.7f / 0.28f);
       }
-      pk[k][2 * j] = pack_bf16x2(v0, v1);
-      pk[k][2 * j + 1] = pack_bf16x2(v2, v3);
+      pw[2 * j] = zero_row ? 0u : pack_bf16x2(v0, v1);
+      pw[2 * j + 1] = zero_row ? 0u : pack_bf16x2(v2, v3);
+    }
+    if (EPI_FAST_BUFS != 3) {
+      // single staging area: the previous block's store has read it; stage, fence, store this block
+      if (t.lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < EPI_CHUNK / 8; ++j)
+        sts128u((wst + t.lane * 64u) | ((j << 4) ^ t.x3), pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_2d_addr(tma_o16, wst, n0 + (2 * k + t.grp) * EPI_CHUNK, m0 + t.q * 32);
+        tma_store_commit();
+      }
     }
   }
-  if (p.valid_rows < p.rows_per_cloud && !row_valid) {  // padding rows are written as exact zeros
+  if (EPI_FAST_BUFS == 3) {
+    __syncwarp();  // lane 0's wait on the previous stores covers the whole warp's staging areas
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int j = 0; j < EPI_CHUNK / 2; ++j) pk[k][j] = 0u;
-  }
-  __syncwarp();  // lane 0's wait on the previous stores covers the whole warp's staging areas
-  const uint32_t wst = stage_base + (uint32_t)(t.grp * 4 + t.q) * 6144u;  // this warp: 3 x (32 rows x 64 B, 64 B swizzle)
+      for (int j = 0; j < EPI_CHUNK / 8; ++j)
+        sts128u((wst + k * 2048u + t.lane * 64u) | ((j << 4) ^ t.x3), pk[EPI_FAST_BUFS == 3 ? k : 0][4 * j], pk[EPI_FAST_BUFS == 3 ? k : 0][4 * j + 1],
+                pk[EPI_FAST_BUFS == 3 ? k : 0][4 * j + 2], pk[EPI_FAST_BUFS == 3 ? k : 0][4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int j = 0; j < EPI_CHUNK / 8; ++j)
-      sts128u((wst + k * 2048u + t.lane * 64u) | ((j << 4) ^ t.x3), pk[k][4 * j], pk[k][4 * j + 1], pk[k][4 * j + 2], pk[k][4 * j + 3]);
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (elect_one()) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) tma_store_2d_addr(tma_o16, wst + k * 2048u, n0 + (2 * k + t.grp) * EPI_CHUNK, m0 + t.q * 32);
-    tma_store_commit();
+      for (int k = 0; k < 3; ++k) tma_store_2d_addr(tma_o16, wst + k * 2048u, n0 + (2 * k + t.grp) * EPI_CHUNK, m0 + t.q * 32);
+      tma_store_commit();
+    }
   }
 }
 

@@ -261,7 +261,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const uint32_t lj = pj ^ rl;                 // logical chunk: channels 8 lj .. 8 lj + 7 of the k-block
     const int K = p.K, gs = K / p.n_groups;
     const double count = (double)p.e.valid_rows * gs;
-    // a / s of a row block from the group statistics; computed one row block ahead, off the critical path
+    // a / s of a row block from the group statistics, computed one row block ahead.  FP64 division and square root cost
+    // thousands of cycles per warp on this part, so the double-precision work is two multiplies and one FMA per channel
+    // (mean = s1 / n and E[x^2] - mean^2 need the precision, rstd does not) and the statistics loads are issued first.
+    const double inv_count = 1.0 / count;
     auto make_norm = [&](int pb, uint32_t buf) {
       const int m0 = pb * 2 * BM + (int)rank * BM;
       const int cloud = m0 / p.e.rows_per_cloud;
@@ -269,14 +272,39 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       float* na = sNorm + buf * 2 * MAX_KB * BK;
       float* ns = na + MAX_KB * BK;
       const float tc = __ldg(p.n_t + (long long)cloud * p.n_t_stride);
-      for (int c = tt; c < K; c += XF_THREADS) {
-        float mean, rstd;
-        group_mean_rstd(cst, c / gs, gs, p.n_stat_gs, count, p.n_eps, mean, rstd);
-        const float sc = tc * __ldg(p.n_scale_w + c) + __ldg(p.n_scale_b + c);
-        const float bi = tc * __ldg(p.n_bias_w + c) + __ldg(p.n_bias_b + c);
-        const float a = sc * rstd;
-        na[c] = a;
-        ns[c] = bi - a * mean;
+      const int per = gs / p.n_stat_gs;
+      // all global loads of this thread's channels first (MAX_KB * BK / XF_THREADS = 6), then the arithmetic: one L2
+      // round trip instead of six
+      constexpr int NCH = MAX_KB * BK / XF_THREADS;
+      double s1[NCH], s2[NCH];
+      float sw[NCH], sb[NCH], bw[NCH], bb[NCH];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = tt + i * XF_THREADS;
+        s1[i] = s2[i] = 0.0;
+        sw[i] = sb[i] = bw[i] = bb[i] = 0.f;
+        if (c < K) {
+          const int g = c / gs;
+          for (int j = 0; j < per; ++j) {
+            s1[i] += cst[(g * per + j) * 2];
+            s2[i] += cst[(g * per + j) * 2 + 1];
+          }
+          sw[i] = __ldg(p.n_scale_w + c); sb[i] = __ldg(p.n_scale_b + c);
+          bw[i] = __ldg(p.n_bias_w + c); bb[i] = __ldg(p.n_bias_b + c);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = tt + i * XF_THREADS;
+        if (c < K) {
+          const double m = s1[i] * inv_count;
+          double var = fma(-m, m, s2[i] * inv_count);
+          if (var < 0.0) var = 0.0;
+          const float rstd = rsqrtf(static_cast<float>(var) + p.n_eps);
+          const float a = (tc * sw[i] + sb[i]) * rstd;
+          na[c] = a;
+          ns[c] = (tc * bw[i] + bb[i]) - a * static_cast<float>(m);
+        }
       }
       named_bar_sync(2, XF_THREADS);  // a / s visible to both warps
     };
