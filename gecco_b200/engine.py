@@ -141,8 +141,17 @@ class Engine:
 
     refresh = invalidate
 
+    def _describe_cached(self):
+        """`_describe` walks the whole module tree; its result is reused while the network still has the very same
+        parameter objects (a cheap walk over ~200 parameters instead of rebuilding the description)."""
+        net = self._network_ref()
+        sig = None if net is None else tuple(id(p) for p in net.parameters())
+        if self._described is None or self._described[0] != sig:
+            self._described = (sig, self._describe())
+        return self._described[1]
+
     def _ensure(self, device: torch.device):
-        desc, net_t, layer_t = self._describe()
+        desc, net_t, layer_t = self._describe_cached()
         tensors = [t for t in net_t if t is not None] + layer_t
         for t in tensors:
             if not t.is_cuda or t.dtype != torch.float32:

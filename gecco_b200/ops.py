@@ -299,9 +299,17 @@ REPARAM_KIND = {"none": 0, "gaussian": 1, "uvl": 2}
 
 
 def reparam(x: Tensor, kind: int, to_data: bool, mean=None, sigma=None, logit_scale: float = 1.1, K: Tensor | None = None) -> Tensor:
-    """reparam.py data_to_diffusion / diffusion_to_data on [B, N, 3] float32 or float64."""
+    """reparam.py data_to_diffusion / diffusion_to_data on [..., 3] float32 or float64 (the reference accepts any leading
+    dimensions: GaussianReparam broadcasts, UVLReparam needs [B, ..., 3] with one camera per leading index)."""
     lib = _lib_for(x)
     assert x.dtype in (torch.float32, torch.float64) and x.shape[-1] == 3
+    shape = x.shape
+    if x.dim() == 1:
+        x = x.view(1, 1, 3)
+    elif x.dim() == 2:
+        x = x.unsqueeze(0) if K is None else x.unsqueeze(1)
+    elif x.dim() > 3:
+        x = x.reshape(shape[0], -1, 3)
     x = x.contiguous()
     out = torch.empty_like(x)
     mean_a = (C.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
@@ -311,7 +319,7 @@ def reparam(x: Tensor, kind: int, to_data: bool, mean=None, sigma=None, logit_sc
     clouds, pts = x.shape[0], x.shape[1]
     _abi.check(lib.gecco_reparam(_ptr(x), _ptr(out), int(x.dtype == torch.float64), kind, int(to_data), mean_a, sig_a,
                                  C.c_float(logit_scale), _ptr(K), clouds, pts, _stream(x)))
-    return out
+    return out.view(shape)
 
 
 def pack_features(f: Tensor, out: Tensor | None = None) -> Tensor:

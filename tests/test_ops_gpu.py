@@ -328,3 +328,24 @@ def test_unpool_attention(cuda, tensor_cores, B, Np):
     ref = F.scaled_dot_product_attention(qr, k, v).transpose(1, 2).reshape(B * Np, C)
     err = (out.float().cpu() - ref).abs().max().item()
     assert err < 3e-2, err
+
+
+def test_reparam_leading_dims(cuda):
+    """The reference's reparams accept any leading dimensions ([..., 3]); the kernel sees them flattened."""
+    from gecco_b200.reparam import GaussianReparam, UVLReparam
+    import gecco_b200 as G
+
+    g = _gen(31)
+    gr = GaussianReparam(torch.tensor([0.0, 0.1, 1.0]), torch.tensor([0.2, 0.3, 0.4])).to(cuda)
+    for shape in [(3,), (7, 3), (2, 5, 3), (2, 3, 4, 3)]:
+        x = torch.randn(*shape, generator=g).to(cuda)
+        d = gr.diffusion_to_data(x, None)
+        assert d.shape == x.shape and torch.allclose(d, x * gr.sigma + gr.mean, atol=1e-6)
+        assert torch.allclose(gr.data_to_diffusion(d, None), x, atol=1e-5)
+    ur = UVLReparam(torch.tensor([0.0, 0.0, 1.38]), torch.tensor([0.56, 0.60, 0.49])).to(cuda)
+    K = torch.tensor([[1.2, 0, 0.5], [0, 1.2, 0.5], [0, 0, 1]]).expand(2, 3, 3).contiguous().to(cuda)
+    ctx = G.Context3d(image=torch.zeros(2, 3, 4, 4, device=cuda), K=K)
+    x = torch.randn(2, 3, 4, 3, generator=g).to(cuda)
+    d = ur.diffusion_to_data(x, ctx)
+    assert d.shape == x.shape and torch.allclose(ur.diffusion_to_data(x.reshape(2, 12, 3), ctx).view(2, 3, 4, 3), d)
+    assert torch.allclose(ur.data_to_diffusion(d, ctx), x, atol=1e-4)
