@@ -157,12 +157,30 @@ class UnpoolArgs(C.Structure):
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("inducers", C.c_int32),
         ("out_bf16", C.c_void_p), ("ldo", C.c_int64),
         ("vt_scratch", C.c_void_p),
+        ("vt_ready", C.c_int32),
     ]
 
 
 MAX_LAYERS = 32
 NW_COUNT = 6
 LW_COUNT = 33
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [
+        ("clouds", C.c_int32), ("inducers", C.c_int32), ("c", C.c_int32), ("hidden", C.c_int32), ("heads", C.c_int32),
+        ("groups", C.c_int32),
+        ("first_stage", C.c_int32),
+        ("partial", C.c_void_p), ("splits", C.c_int32),
+        ("pooled", C.c_void_p),
+        ("w_pool_out", C.c_void_p), ("w_mlp0", C.c_void_p), ("w_mlp2", C.c_void_p), ("w_kv", C.c_void_p),
+        ("b_mlp0", C.c_void_p), ("b_mlp2", C.c_void_p), ("b_kv", C.c_void_p),
+        ("act_alpha", C.c_float),
+        ("norm", (C.c_void_p * 4) * 2),
+        ("t", C.c_void_p), ("t_stride", C.c_int32), ("eps", C.c_float),
+        ("hn", C.c_void_p), ("hh", C.c_void_p), ("h3", C.c_void_p), ("khv", C.c_void_p), ("vt", C.c_void_p),
+        ("cache_out", C.c_void_p),
+    ]
 
 
 class ModelDesc(C.Structure):

@@ -378,6 +378,12 @@ static bool pool_tc_enabled() {
   return !(v != nullptr && v[0] == '0');
 }
 
+int launch_pool_attention_partial(const gecco_pool_args& a, cudaStream_t s, int* splits_used) {
+  *splits_used = 1;
+  if (pool_tc_enabled() && pool_tc_supported(a)) return launch_pool_tc(a, s, splits_used);
+  return launch_pool_attention(a, s);
+}
+
 int launch_pool_attention(const gecco_pool_args& a, cudaStream_t s) {
   if (pool_tc_enabled() && pool_tc_supported(a)) {
     int nsplit = 1;
@@ -473,4 +479,15 @@ extern "C" int gecco_pool_attention(const gecco_pool_args* a, void* stream) {
 extern "C" int gecco_unpool_attention(const gecco_unpool_args* a, void* stream) {
   if (!a) { gecco::set_error("gecco_unpool_attention: null args"); return GECCO_ERR_INVALID; }
   return gecco::launch_unpool_attention(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gecco_pool_attention_partial(const gecco_pool_args* args, int32_t* splits_used, void* stream) {
+  if (args == nullptr || splits_used == nullptr) {
+    gecco::set_error("gecco_pool_attention_partial: null args");
+    return GECCO_ERR_INVALID;
+  }
+  int used = 1;
+  const int rc = gecco::launch_pool_attention_partial(*args, static_cast<cudaStream_t>(stream), &used);
+  *splits_used = used;
+  return rc;
 }

@@ -342,8 +342,10 @@ int launch_unpool_tc(const gecco_unpool_args& a, cudaStream_t stream) {
   GECCO_REQUIRE(unpool_tc_supported(a), "unpool attention (tcgen05): unsupported shape");
   const long long rows = (long long)a.clouds * a.rows_per_cloud;
   __nv_bfloat16* vt = static_cast<__nv_bfloat16*>(a.vt_scratch);
-  launch_pdl(transpose_v_kernel, dim3(a.clouds, 2), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(a.kv), a.ldkv, a.v_off, vt);
-  GECCO_CHECK_LAUNCH("transpose_v_kernel");
+  if (!a.vt_ready) {
+    launch_pdl(transpose_v_kernel, dim3(a.clouds, 2), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(a.kv), a.ldkv, a.v_off, vt);
+    GECCO_CHECK_LAUNCH("transpose_v_kernel");
+  }
 
   CUtensorMap tq, tk, tvt, ty;
   if (int rc = make_tmap_bf16(&tq, a.q, C, rows, a.ldq, TM)) return rc;

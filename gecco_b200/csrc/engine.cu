@@ -278,6 +278,16 @@ int anorm_mode() {
 }
 bool anorm_enabled() { return anorm_mode() != 0; }
 
+// gecco_set_option("chain", 0) / GECCO_CHAIN=0: the inducer side as separate GEMM / AdaGN launches (A/B measurements, tests)
+int g_chain_enabled = -1;
+bool chain_enabled() {
+  if (g_chain_enabled < 0) {
+    const char* v = getenv("GECCO_CHAIN");
+    g_chain_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return g_chain_enabled != 0;
+}
+
 bool fused_mlp_enabled() {
   static const bool on = [] {
     const char* v = getenv("GECCO_FUSED_MLP");
@@ -412,16 +422,43 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       g.out_bf16 = w.big + r0; g.ldo16 = C3;
       TRYP(K_GEMM_KVQ, 2 * Mv * Cd * (C3 - r0), Mv * (Cd * 2 + (C3 - r0) * 2.0) + 2.0 * clouds * (C3 - r0) * Cd, launch_gemm(g, s));
     }
-    if (pooling) {
+    gecco_pool_args pool = {};
+    pool.kv = w.big; pool.ld = C3; pool.k_off = 0; pool.v_off = C;
+    pool.clouds = clouds; pool.rows_per_cloud = Np; pool.valid_rows = points;
+    pool.heads = H; pool.head_dim = hd; pool.inducers = I;
+    pool.q_inducers = L.q_ind;
+    pool.splits = w.splits; pool.partial = w.partial;
+    pool.out_bf16 = w.pooled; pool.ldo = C;
+    // the inducer side in one cluster kernel (inducer_chain.cu) where the shape allows
+    gecco_chain_args ch = {};
+    ch.clouds = clouds; ch.inducers = I; ch.c = C; ch.hidden = hid; ch.heads = H; ch.groups = sg;
+    ch.pooled = w.pooled;
+    ch.w_pool_out = L.pool_out_w; ch.w_mlp0 = L.bmlp_w0; ch.w_mlp2 = L.bmlp_w2; ch.w_kv = L.kv_w;
+    ch.b_mlp0 = lw[GECCO_LW_BMLP_B0]; ch.b_mlp2 = lw[GECCO_LW_BMLP_B2]; ch.b_kv = lw[GECCO_LW_UNPOOL_IN_B] + C;
+    ch.act_alpha = L.bmlp_alpha;
+    for (int i = 0; i < 4; ++i) { ch.norm[0][i] = lw[GECCO_LW_N1 + i]; ch.norm[1][i] = lw[GECCO_LW_N2 + i]; }
+    ch.t = w.c_noise; ch.t_stride = 1; ch.eps = 1e-5f;
+    ch.hn = w.hn; ch.hh = w.hh; ch.h3 = w.h3; ch.khv = w.khv; ch.vt = w.vt;
+    const bool chain = chain_enabled() && inducer_chain_supported(ch);
+    bool kv_done = false;
+    if (pooling && chain) {
+      int nsplit = 1;
+      // few key splits are merged by the chain kernel itself; many (small batches: up to one split per 128-point tile) by
+      // the wide merge kernel, which spreads them over the whole machine
+      if (pool.splits <= 4) {
+        TRYP(K_POOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 2, launch_pool_attention_partial(pool, s, &nsplit));
+      } else {
+        TRYP(K_POOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 2, launch_pool_attention(pool, s));
+      }
+      ch.first_stage = 0;
+      ch.partial = w.partial; ch.splits = nsplit;
+      if (cache_out != nullptr) ch.cache_out = cache_out + (size_t)l * irows * C;
+      TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd * (2 * Cd + 2 * Hd) + 2 * Mi * Cd * 2 * Cd, Mi * Cd * 8 + 2 * (2 * Cd * Cd + 2 * Cd * Hd + 2 * Cd * Cd),
+           launch_inducer_chain(ch, s));
+      kv_done = true;
+    } else if (pooling) {
       // AttentionPool (:47-65)
-      gecco_pool_args p = {};
-      p.kv = w.big; p.ld = C3; p.k_off = 0; p.v_off = C;
-      p.clouds = clouds; p.rows_per_cloud = Np; p.valid_rows = points;
-      p.heads = H; p.head_dim = hd; p.inducers = I;
-      p.q_inducers = L.q_ind;
-      p.splits = w.splits; p.partial = w.partial;
-      p.out_bf16 = w.pooled; p.ldo = C;
-      TRYP(K_POOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 2, launch_pool_attention(p, s));
+      TRYP(K_POOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 2, launch_pool_attention(pool, s));
       gecco_gemm_args g = gemm_base(w.pooled, C, L.pool_out_w, C, irows, C, C, I, I);
       g.out_f32 = w.h; g.ldo32 = C; g.stats = stat(l, 1);
       TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd * Cd, Mi * Cd * 6 + 2 * Cd * Cd, launch_gemm(g, s));
@@ -447,18 +484,26 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cache_in + (size_t)l * irows * C, w.h3, n, 1.0f);
       prof_end(s);
       GECCO_CHECK_LAUNCH("pack_bf16_kernel(cache)");
+      if (chain) {
+        ch.first_stage = 3;
+        TRYP(K_INDUCER_CHAIN, 4 * Mi * Cd * Cd, Mi * Cd * 6 + 4 * Cd * Cd, launch_inducer_chain(ch, s));
+        kv_done = true;
+      }
     }
     // unpool = nn.MultiheadAttention(query=y, key=value=h)  (:112)
     {
-      gecco_gemm_args g = gemm_base(w.h3, C, L.kv_w, C, irows, 2 * C, C, I, I);
-      g.bias = lw[GECCO_LW_UNPOOL_IN_B] + C;
-      g.out_bf16 = w.khv; g.ldo16 = 2 * C;
-      TRYP(K_INDUCER_CHAIN, 4 * Mi * Cd * Cd, Mi * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
+      gecco_gemm_args g;
+      if (!kv_done) {
+        g = gemm_base(w.h3, C, L.kv_w, C, irows, 2 * C, C, I, I);
+        g.bias = lw[GECCO_LW_UNPOOL_IN_B] + C;
+        g.out_bf16 = w.khv; g.ldo16 = 2 * C;
+        TRYP(K_INDUCER_CHAIN, 4 * Mi * Cd * Cd, Mi * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
+      }
       gecco_unpool_args u = {};
       u.q = w.big + 2 * C; u.ldq = C3; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
       u.clouds = clouds; u.rows_per_cloud = Np; u.heads = H; u.head_dim = hd; u.inducers = I;
       u.out_bf16 = w.y; u.ldo = C;
-      u.vt_scratch = w.vt;
+      u.vt_scratch = w.vt; u.vt_ready = kv_done ? 1 : 0;
       TRYP(K_UNPOOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 4, launch_unpool_attention(u, s));
       // x = x + out_proj(attn)  (:164), bf16 copy, statistics for mlp_norm
       g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);
@@ -754,7 +799,7 @@ std::vector<unsigned char> sample_key(const gecco_sample_args* a) {
   put(&a->latents, sizeof(void*)); put(&a->noise, sizeof(void*)); put(&a->x_out, sizeof(void*));
   put(&a->ctx, sizeof(gecco_context));
   put(&a->workspace, sizeof(void*)); put(&a->workspace_bytes, sizeof(int64_t));
-  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1);
+  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1) | ((chain_enabled() ? 1 : 0) << 2);
   put(&fused, sizeof(int));
   return k;
 }
@@ -770,6 +815,7 @@ void drop_graph(gecco_engine* e, size_t i) {
 }  // namespace
 void set_graphs_option(int value) { g_graphs_enabled = value != 0 ? 1 : 0; }
 void set_anorm_option(int value) { g_anorm_enabled = value != 0 ? 1 : 0; }
+void set_chain_option(int value) { g_chain_enabled = value != 0 ? 1 : 0; }
 }  // namespace gecco
 
 namespace gecco {
@@ -898,7 +944,7 @@ extern "C" int gecco_upsample_step(gecco_engine* e, const gecco_upsample_step_ar
   std::vector<unsigned char> key(sizeof(gecco_upsample_step_args) + 8);
   memcpy(key.data(), a, sizeof(gecco_upsample_step_args));
   memcpy(key.data() + sizeof(gecco_upsample_step_args), "upsample", 8);
-  key.push_back((unsigned char)((fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1)));
+  key.push_back((unsigned char)((fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1) | ((chain_enabled() ? 1 : 0) << 2)));
   return run_graphed(e, key, static_cast<cudaStream_t>(stream), [&](cudaStream_t s) { return enqueue_upsample_step(e, a, s); });
 }
 

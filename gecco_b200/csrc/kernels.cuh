@@ -24,6 +24,7 @@ void set_fast_epilogue_option(int value);  // gemm_pair.cu: gecco_set_option("fa
 
 int launch_gemm(const gecco_gemm_args& a, cudaStream_t s);
 void set_graphs_option(int value);
+void set_chain_option(int value);  // engine.cu: gecco_set_option("chain", v)
 void set_anorm_option(int value);  // engine.cu: gecco_set_option("anorm", v)  // engine.cu: gecco_set_option("graphs", v)
 // Fused MLP (mlp_fused.cu): GEMM -> Gaussian activation -> GEMM -> + residual with the hidden tensor on chip.
 bool mlp_fused_supported(const gecco_mlp_args& a);
@@ -52,5 +53,12 @@ int launch_unpool_tc(const gecco_unpool_args& a, cudaStream_t s);
 // key-split partials in a.partial (pool_combine_kernel finishes); 1: a.out_bf16 is final.
 bool pool_tc_supported(const gecco_pool_args& a);
 int launch_pool_tc(const gecco_pool_args& a, cudaStream_t s, int* splits_used);
+
+// Inducer side of a Broadcast layer in one cluster kernel (inducer_chain.cu).
+bool inducer_chain_supported(const gecco_chain_args& a);
+int launch_inducer_chain(const gecco_chain_args& a, cudaStream_t s);
+// Pool attention without the final merge of the key splits: *splits_used > 1 means a.partial holds the partials (the
+// inducer chain merges them), 1 means a.out_bf16 is final.
+int launch_pool_attention_partial(const gecco_pool_args& a, cudaStream_t s, int* splits_used);
 
 }  // namespace gecco

@@ -409,6 +409,66 @@ def pool_attention(kv: Tensor, q_inducers: Tensor, *, clouds: int, rows_per_clou
     return out
 
 
+def pool_attention_partial(kv: Tensor, q_inducers: Tensor, *, clouds: int, rows_per_cloud: int, valid_rows: int, heads: int,
+                           head_dim: int, k_off: int, v_off: int, splits: int = 1):
+    """Pool attention core without the merge of the key splits (gecco_pool_attention_partial).  Returns (partial fp32
+    scratch, splits_used) when splits_used > 1, else (pooled bf16, 1)."""
+    lib = _lib_for(kv)
+    inducers = q_inducers.shape[1]
+    partial = torch.empty((clouds * heads * splits * inducers * (head_dim + 2),), device=kv.device, dtype=torch.float32)
+    out = torch.empty((clouds * inducers, heads * head_dim), device=kv.device, dtype=torch.bfloat16)
+    a = _abi.PoolArgs()
+    a.kv, a.ld, a.k_off, a.v_off = kv.data_ptr(), kv.stride(0), k_off, v_off
+    a.clouds, a.rows_per_cloud, a.valid_rows = clouds, rows_per_cloud, valid_rows
+    a.heads, a.head_dim, a.inducers = heads, head_dim, inducers
+    a.q_inducers = q_inducers.data_ptr()
+    a.splits, a.partial = splits, partial.data_ptr()
+    a.out_bf16, a.ldo = out.data_ptr(), out.stride(0)
+    used = C.c_int32(1)
+    _abi.check(lib.gecco_pool_attention_partial(C.byref(a), C.byref(used), _stream(kv)))
+    return (partial, used.value) if used.value > 1 else (out, 1)
+
+
+def inducer_chain(pooled: Tensor, w_pool_out: Tensor, norm1: list[Tensor], w_mlp0: Tensor, b_mlp0: Tensor, act_alpha: float,
+                  w_mlp2: Tensor, b_mlp2: Tensor, norm2: list[Tensor], w_kv: Tensor, b_kv: Tensor, t: Tensor, *,
+                  partial: Tensor | None = None, splits: int = 1, eps: float = 1e-5, want_cache: bool = True, first_stage: int = 0):
+    """Inducer side of one Broadcast layer in one launch (gecco_inducer_chain).  pooled: bf16 [clouds*64, C] (input when
+    splits <= 1, scratch otherwise); weights bf16 [n_out, k]; norm1 / norm2: [scale.weight, scale.bias, bias.weight,
+    bias.bias] fp32 [C]; t: fp32 [clouds].  Returns (h3 bf16 [clouds*64, C], khv bf16 [clouds*64, 2C], vt bf16 [clouds, C, 64],
+    cache fp32 [clouds*64, C] or None).  first_stage = 3: `pooled` is taken as h3 (bf16 cached inducer states)."""
+    lib = _lib_for(pooled)
+    m, c = pooled.shape
+    clouds = m // 64
+    hid = w_mlp0.shape[0]
+    dev = pooled.device
+    bf = torch.bfloat16
+    for w in (pooled, w_pool_out, w_mlp0, w_mlp2, w_kv):
+        assert w.dtype == bf and w.is_contiguous()
+    hn = torch.empty((m, c), device=dev, dtype=bf)
+    hh = torch.empty((m, hid), device=dev, dtype=bf)
+    h3 = pooled if first_stage == 3 else torch.empty((m, c), device=dev, dtype=bf)
+    khv = torch.empty((m, 2 * c), device=dev, dtype=bf)
+    vt = torch.empty((clouds, c, 64), device=dev, dtype=bf)
+    cache = torch.empty((m, c), device=dev, dtype=torch.float32) if (want_cache and first_stage == 0) else None
+    a = _abi.ChainArgs()
+    a.clouds, a.inducers, a.c, a.hidden, a.heads, a.groups = clouds, 64, c, hid, 8, 32
+    a.first_stage = first_stage
+    a.partial, a.splits = _ptr(partial), splits
+    a.pooled = pooled.data_ptr()
+    a.w_pool_out, a.w_mlp0, a.w_mlp2, a.w_kv = w_pool_out.data_ptr(), w_mlp0.data_ptr(), w_mlp2.data_ptr(), w_kv.data_ptr()
+    a.b_mlp0, a.b_mlp2, a.b_kv = b_mlp0.data_ptr(), b_mlp2.data_ptr(), b_kv.data_ptr()
+    a.act_alpha = act_alpha
+    for n, ws in enumerate((norm1, norm2)):
+        for i in range(4):
+            assert ws[i].dtype == torch.float32 and ws[i].is_contiguous()
+            a.norm[n][i] = ws[i].data_ptr()
+    a.t, a.t_stride, a.eps = t.data_ptr(), t.stride(0) if t.dim() > 0 else 0, eps
+    a.hn, a.hh, a.h3, a.khv, a.vt = hn.data_ptr(), hh.data_ptr(), h3.data_ptr(), khv.data_ptr(), vt.data_ptr()
+    a.cache_out = _ptr(cache)
+    _abi.check(lib.gecco_inducer_chain(C.byref(a), _stream(pooled)))
+    return h3, khv, vt, cache
+
+
 def unpool_attention(q: Tensor, khv: Tensor, *, clouds: int, rows_per_cloud: int, heads: int, head_dim: int, v_off: int,
                      inducers: int = 64, out: Tensor | None = None, tensor_cores: bool = True) -> Tensor:
     """Attention core of the unpool MultiheadAttention; with tensor_cores the tcgen05 / TMEM kernel is used where it

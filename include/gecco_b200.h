@@ -280,6 +280,9 @@ typedef struct gecco_pool_args {
   void* out_bf16; int64_t ldo;
 } gecco_pool_args;
 int gecco_pool_attention(const gecco_pool_args* args, void* stream);
+/* The same without the final merge of the key splits: *splits_used > 1 means args->partial holds that many (acc, max, sum)
+ * partials per (cloud, head, inducer) for gecco_inducer_chain to merge; 1 means args->out_bf16 is final. */
+int gecco_pool_attention_partial(const gecco_pool_args* args, int32_t* splits_used, void* stream);
 
 /* Attention core of Broadcast.unpool = nn.MultiheadAttention(query=points, key=value=inducers)
  * (models/set_transformer.py:90,112) between the in- and out-projections: per head
@@ -295,8 +298,35 @@ typedef struct gecco_unpool_args {
   void* vt_scratch;   /* optional bf16 [clouds * heads * head_dim * inducers] device scratch (v transposed per cloud): when given
                        * and heads == 8, head_dim == 48, rows_per_cloud % 128 == 0 the tcgen05 / TMEM kernel runs, otherwise
                        * (NULL or other shapes) the mma.sync kernel */
+  int32_t vt_ready;   /* nonzero: vt_scratch already holds V transposed (written by gecco_inducer_chain) */
 } gecco_unpool_args;
 int gecco_unpool_attention(const gecco_unpool_args* args, void* stream);
+
+/* The inducer side of Broadcast.forward (models/set_transformer.py:106-112) in one launch:
+ *   pooled (or the key-split partials of gecco_pool_attention) -> pool.out_proj -> norm_1 (AdaGN) -> mlp
+ *   (Linear, Gaussian activation, Linear) -> norm_2 (AdaGN) -> unpool key | value in-projection (+ V transposed per cloud).
+ * A cluster of four CTAs owns two clouds; the AdaGN statistics over (64 inducers, 12 channels) are computed inside the
+ * producing accumulator tile.  Shapes: 64 inducers, C = 384, hidden = 768, 8 heads, 32 groups (gecco-torch's only
+ * configuration); gecco_inducer_chain returns GECCO_ERR_INVALID for anything else (the engine then runs the stages as
+ * separate gecco_gemm / gecco_adagn launches).
+ * first_stage 0: the whole chain; 3: only h3 -> k | v (the caller put the cached inducer states, bf16, into h3).
+ * Weights are bf16 [n_out, k] row-major (nn.Linear layout); all activation buffers are bf16 [clouds*64, C or hidden]:
+ * pooled / hn / h3 [.., C], hh [.., hidden], khv [.., 2C] (k | v); vt: optional bf16 [clouds][C][64]; cache_out: optional
+ * fp32 [clouds*64, C] copy of the norm_2 output (the `hs` entry of SetTransformer.forward, :211). */
+typedef struct gecco_chain_args {
+  int32_t clouds, inducers, c, hidden, heads, groups;
+  int32_t first_stage;
+  const float* partial; int32_t splits;   /* splits <= 1: pooled is final */
+  void* pooled;
+  const void *w_pool_out, *w_mlp0, *w_mlp2, *w_kv;
+  const float *b_mlp0, *b_mlp2, *b_kv;
+  float act_alpha;
+  const float* norm[2][4];                /* norm_1 / norm_2: scale.weight, scale.bias, bias.weight, bias.bias, [C] each */
+  const float* t; int32_t t_stride; float eps;
+  void *hn, *hh, *h3, *khv, *vt;
+  float* cache_out;
+} gecco_chain_args;
+int gecco_inducer_chain(const gecco_chain_args* args, void* stream);
 
 /* ========================================================================
  * Denoiser engine: one handle per (model, device).  This is the entry a maintainer binds in place of
