@@ -59,6 +59,8 @@ class MlpArgs(C.Structure):
         ("out_f32", C.c_void_p), ("ldo32", C.c_int64),
         ("out_bf16", C.c_void_p), ("ldo16", C.c_int64),
         ("stats", C.c_void_p),
+        ("anorm", ANorm),
+        ("scratch", C.c_void_p),
     ]
 
 

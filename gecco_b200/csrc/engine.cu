@@ -288,6 +288,16 @@ bool chain_enabled() {
   return g_chain_enabled != 0;
 }
 
+// gecco_set_option("mlp_pair", 0) / GECCO_MLP_PAIR=0: the point-side MLP as two GEMMs with the hidden tensor in HBM
+int g_mlp_pair_enabled = -1;
+bool mlp_pair_enabled() {
+  if (g_mlp_pair_enabled < 0) {
+    const char* v = getenv("GECCO_MLP_PAIR");
+    g_mlp_pair_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return g_mlp_pair_enabled != 0;
+}
+
 bool fused_mlp_enabled() {
   static const bool on = [] {
     const char* v = getenv("GECCO_FUSED_MLP");
@@ -516,7 +526,25 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     // x = x + mlp(AdaGN_mlp(x, t))  (:165-166): mlp_norm folded into mlp.0; statistics for the next broadcast_norm /
     // the head norm
     double* const next_stats = (l + 1 < d.n_layers) ? stat(l + 1, 0) : head_stats;
+    gecco_mlp_args mp = {};
     if (an) {
+      mp.a = w.xb; mp.lda = C;
+      mp.w1 = L.mlp_w0; mp.ldw1 = C; mp.b1 = lw[GECCO_LW_MLP_B0];
+      mp.act_alpha = L.mlp_alpha;
+      mp.w2 = L.mlp_w2; mp.ldw2 = hid; mp.b2 = lw[GECCO_LW_MLP_B2];
+      mp.m = rows; mp.c = C; mp.hidden = hid; mp.rows_per_cloud = Np; mp.valid_rows = points;
+      mp.res = w.x; mp.ldr = C; mp.out_f32 = w.x; mp.ldo32 = C; mp.out_bf16 = xb_out; mp.ldo16 = C;
+      mp.stats = next_stats;
+      mp.anorm.stats = stat(l, 3); mp.anorm.stat_gs = C / sg; mp.anorm.groups = sg; mp.anorm.eps = 1e-5f;
+      mp.anorm.t = w.c_noise; mp.anorm.t_stride = 1;
+      mp.anorm.scale_w = lw[GECCO_LW_MN]; mp.anorm.scale_b = lw[GECCO_LW_MN + 1];
+      mp.anorm.bias_w = lw[GECCO_LW_MN + 2]; mp.anorm.bias_b = lw[GECCO_LW_MN + 3];
+      mp.scratch = w.big;  // k | v | q of this layer have been consumed
+    }
+    if (an && mlp_pair_enabled() && mlp_pair_supported(mp)) {
+      // one kernel: AdaGN on the A operand, the hidden tile of a row block parked in L2 between the products (mlp_pair.cu)
+      TRYP(K_MLP_FUSED, 4 * Mv * Cd * Hd, Mv * Cd * 12 + 4 * Cd * Hd, launch_mlp_pair(mp, s));
+    } else if (an) {
       gecco_gemm_args g = gemm_base(w.xb, C, L.mlp_w0, C, rows, hid, C, Np, points);
       set_anorm(g, lw + GECCO_LW_MN, stat(l, 3));
       g.bias = lw[GECCO_LW_MLP_B0]; g.bias_stride = 0; g.act = 1; g.act_alpha = L.mlp_alpha;
@@ -799,7 +827,7 @@ std::vector<unsigned char> sample_key(const gecco_sample_args* a) {
   put(&a->latents, sizeof(void*)); put(&a->noise, sizeof(void*)); put(&a->x_out, sizeof(void*));
   put(&a->ctx, sizeof(gecco_context));
   put(&a->workspace, sizeof(void*)); put(&a->workspace_bytes, sizeof(int64_t));
-  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1) | ((chain_enabled() ? 1 : 0) << 2);
+  const int fused = (fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1) | ((chain_enabled() ? 1 : 0) << 2) | ((mlp_pair_enabled() ? 1 : 0) << 3);
   put(&fused, sizeof(int));
   return k;
 }
@@ -816,6 +844,7 @@ void drop_graph(gecco_engine* e, size_t i) {
 void set_graphs_option(int value) { g_graphs_enabled = value != 0 ? 1 : 0; }
 void set_anorm_option(int value) { g_anorm_enabled = value != 0 ? 1 : 0; }
 void set_chain_option(int value) { g_chain_enabled = value != 0 ? 1 : 0; }
+void set_mlp_pair_option(int value) { g_mlp_pair_enabled = value != 0 ? 1 : 0; }
 }  // namespace gecco
 
 namespace gecco {
@@ -944,7 +973,7 @@ extern "C" int gecco_upsample_step(gecco_engine* e, const gecco_upsample_step_ar
   std::vector<unsigned char> key(sizeof(gecco_upsample_step_args) + 8);
   memcpy(key.data(), a, sizeof(gecco_upsample_step_args));
   memcpy(key.data() + sizeof(gecco_upsample_step_args), "upsample", 8);
-  key.push_back((unsigned char)((fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1) | ((chain_enabled() ? 1 : 0) << 2)));
+  key.push_back((unsigned char)((fused_mlp_enabled() ? 1 : 0) | (anorm_mode() << 1) | ((chain_enabled() ? 1 : 0) << 2) | ((mlp_pair_enabled() ? 1 : 0) << 3)));
   return run_graphed(e, key, static_cast<cudaStream_t>(stream), [&](cudaStream_t s) { return enqueue_upsample_step(e, a, s); });
 }
 

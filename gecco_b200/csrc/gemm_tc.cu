@@ -413,6 +413,10 @@ extern "C" int gecco_set_option(const char* name, int value) {
     gecco::set_anorm_option(value);
     return GECCO_OK;
   }
+  if (name != nullptr && strcmp(name, "mlp_pair") == 0) {
+    gecco::set_mlp_pair_option(value);
+    return GECCO_OK;
+  }
   if (name != nullptr && strcmp(name, "chain") == 0) {
     gecco::set_chain_option(value);
     return GECCO_OK;

@@ -29,6 +29,10 @@ void set_anorm_option(int value);  // engine.cu: gecco_set_option("anorm", v)  /
 // Fused MLP (mlp_fused.cu): GEMM -> Gaussian activation -> GEMM -> + residual with the hidden tensor on chip.
 bool mlp_fused_supported(const gecco_mlp_args& a);
 int launch_mlp_fused(const gecco_mlp_args& a, cudaStream_t s);
+// CTA-pair MLP with the hidden tile parked in an L2-resident scratch and AdaGN on the A operand (mlp_pair.cu).
+bool mlp_pair_supported(const gecco_mlp_args& a);
+int launch_mlp_pair(const gecco_mlp_args& a, cudaStream_t s);
+void set_mlp_pair_option(int value);  // engine.cu: gecco_set_option("mlp_pair", v)
 int launch_group_stats(const float* x, long long ldx, int clouds, int rows_per_cloud, int valid_rows, int C, int gs,
                        double* stats, cudaStream_t s);
 int launch_adagn(const gecco_adagn_args& a, cudaStream_t s);

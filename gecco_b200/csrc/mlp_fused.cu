@@ -471,5 +471,6 @@ int launch_mlp_fused(const gecco_mlp_args& a, cudaStream_t stream) {
 
 extern "C" int gecco_mlp(const gecco_mlp_args* args, void* stream) {
   GECCO_REQUIRE(args != nullptr, "gecco_mlp: null args");
+  if (args->anorm.stats != nullptr) return gecco::launch_mlp_pair(*args, static_cast<cudaStream_t>(stream));
   return gecco::launch_mlp_fused(*args, static_cast<cudaStream_t>(stream));
 }

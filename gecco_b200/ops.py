@@ -124,7 +124,7 @@ def set_option(name: str, value: int) -> None:
 def mlp(a: Tensor, w1: Tensor, b1: Tensor, act_alpha: float, w2: Tensor, b2: Tensor, res: Tensor, *,
         out_f32: Tensor | None = None, out_bf16: Tensor | bool | None = None, stats: Tensor | None = None,
         rows_per_cloud: int | None = None, valid_rows: int | None = None, w1_rows_per_cloud: int = 0,
-        b1_stride: int = 0):
+        b1_stride: int = 0, anorm: dict | None = None):
     """out = res + w2 @ g(w1_cloud @ a + b1_cloud) + b2 with the hidden activation kept on chip; see gecco_mlp in
     include/gecco_b200.h (models/set_transformer.py:165-166)."""
     lib = _lib_for(a)
@@ -161,6 +161,16 @@ def mlp(a: Tensor, w1: Tensor, b1: Tensor, act_alpha: float, w2: Tensor, b2: Ten
     if stats is not None:
         assert stats.dtype == torch.float64 and stats.is_contiguous()
         args.stats = stats.data_ptr()
+    scratch = None
+    if anorm is not None:  # AdaGN on the A operand: the CTA-pair kernel with the hidden tile parked in an L2-resident scratch
+        n = args.anorm
+        n.stats, n.stat_gs, n.groups, n.eps = anorm["stats"].data_ptr(), anorm.get("stat_gs", STAT_GS), anorm["groups"], anorm.get("eps", 1e-5)
+        n.t, n.t_stride = anorm["t"].data_ptr(), 1
+        n.scale_w, n.scale_b = anorm["scale_w"].data_ptr(), anorm["scale_b"].data_ptr()
+        n.bias_w, n.bias_b = anorm["bias_w"].data_ptr(), anorm["bias_b"].data_ptr()
+        sms = torch.cuda.get_device_properties(a.device).multi_processor_count
+        scratch = torch.empty((min(m, 128 * sms), hidden), device=a.device, dtype=torch.bfloat16)
+        args.scratch = scratch.data_ptr()
     _abi.check(lib.gecco_mlp(C.byref(args), _stream(a)))
     return out_f32, out_bf16
 

@@ -112,6 +112,8 @@ int gecco_gemm_anorm_supported(int32_t m, int32_t rows_per_cloud, int32_t n_out,
  * res / out_f32 (may alias), out_bf16, stats, rows_per_cloud, valid_rows as in gecco_gemm.
  * Supported shapes: c == 384, hidden % 128 == 0, m % 256 == 0, rows_per_cloud % 256 == 0
  * (GECCO_ERR_INVALID otherwise; the engine then runs the two projections through gecco_gemm).
+ * With args->anorm (hidden == 768) the CTA-pair kernel of mlp_pair.cu runs: AdaGN on the A operand, the hidden tile of
+ * a row block parked in an L2-resident scratch between the two products.
  * ------------------------------------------------------------------------ */
 typedef struct gecco_mlp_args {
   const void* a;   int64_t lda;
@@ -126,6 +128,11 @@ typedef struct gecco_mlp_args {
   float* out_f32;  int64_t ldo32;
   void* out_bf16;  int64_t ldo16;
   double* stats;
+  gecco_anorm anorm;  /* anorm.stats != NULL: `a` is the un-normalised bf16 residual-stream copy and AdaGN (mlp_norm,
+                       * set_transformer.py:165) is applied to the A operand inside the kernel (w1 / b1 shared by all clouds,
+                       * w1_rows_per_cloud == 0); needs `scratch` */
+  void* scratch;      /* anorm path: bf16 device scratch of min(m, 128 * #SMs) x hidden elements: the hidden activation of
+                       * the row block a CTA is working on (rewritten every row block: L2-resident, never read after the call) */
 } gecco_mlp_args;
 
 int gecco_mlp(const gecco_mlp_args* args, void* stream);
