@@ -476,6 +476,54 @@ head_kernel(const gecco_head_args a) {
 
   const int rb = (blockIdx.x * HEAD_WARPS + warp) * HEAD_ROWS_PER_WARP;
   const float* xc = a.x + (long long)cloud * a.rows_per_cloud * a.ldx + lane * 4;
+  if (a.norm != 1) {
+    // four rows in flight; the twelve dot products are reduced together (reduce-scatter: 16 shuffles for four rows,
+    // the sum of value j lands in lanes 2 j and 2 j + 1) and lanes 8 u + 2 o finish output o of row u
+#pragma unroll 1
+    for (int rr = 0; rr < HEAD_ROWS_PER_WARP; rr += 4) {
+      const int r0 = rb + rr;
+      if (r0 >= a.valid_rows) break;
+      float4 v[4][NQ];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+          v[u][i] = r0 + u < a.valid_rows ? __ldg(reinterpret_cast<const float4*>(xc + (long long)(r0 + u) * a.ldx + i * 128))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      float f[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < NQ; ++i)
+            acc += v[u][i].x * w[o][i].x + v[u][i].y * w[o][i].y + v[u][i].z * w[o][i].z + v[u][i].w * w[o][i].w;
+          f[4 * u + o] = acc;
+        }
+        f[4 * u + 3] = 0.f;
+      }
+#pragma unroll
+      for (int half = 8; half >= 1; half >>= 1) {
+        const int off = 2 * half;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? f[i] : f[i + half];
+          const float keep = upper ? f[i + half] : f[i];
+          f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      const float tot = f[0] + __shfl_xor_sync(0xffffffffu, f[0], 1);
+      const int u = lane >> 3, o = (lane >> 1) & 3;
+      if ((lane & 1) == 0 && o < 3 && r0 + u < a.valid_rows) {
+        const float k = o == 0 ? kc[0] : (o == 1 ? kc[1] : kc[2]);
+        const float F = tot - (a.norm == 2 ? k : 0.f) + __ldg(a.b_out + o);
+        head_finish(a, ((long long)cloud * a.valid_rows + r0 + u) * 3 + o, F, c_skip, c_out);
+      }
+    }
+    return;
+  }
 #pragma unroll 1
   for (int rr = 0; rr < HEAD_ROWS_PER_WARP; rr += 2) {
     const int r0 = rb + rr;
