@@ -287,6 +287,8 @@ def load() -> C.CDLL:
     lib.gecco_upsample_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.gecco_upsample_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gecco_graph_status.argtypes = [C.c_void_p]
+    lib.gecco_adam_ema_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,
+                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.gecco_graph_status.restype = C.c_int
     _lib = lib
     return lib

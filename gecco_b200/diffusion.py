@@ -41,6 +41,14 @@ class EDMPrecond(nn.Module):
 
     def forward(self, x: Tensor, sigma: Tensor, raw_context: Any, post_context: Any, do_cache: bool = False,
                 cache: list[Tensor] | None = None):
+        if self.training and torch.is_grad_enabled():
+            # training (model.train() with autograd on): the differentiable path, training.py (tcgen05 GEMMs for the
+            # projections' forward and input gradients); the fused sampling engine below is forward-only
+            if do_cache or cache is not None:
+                raise ValueError("gecco_b200: the inducer cache belongs to sampling; call it under torch.no_grad() / eval()")
+            from . import training
+
+            return training.precond_forward(self, x, sigma, raw_context, post_context)
         K = raw_context.K if raw_context is not None else None
         out, out_cache = engine_for(self.model, self.sigma_data).denoise(
             x, sigma, post_context=post_context, K=K, cache=cache, do_cache=do_cache, mode=1)
@@ -75,8 +83,8 @@ class LogUniformSchedule(nn.Module):
 
 
 class EDMLoss(nn.Module):
-    """Weighted denoising loss (diffusion.py:118-143).  The CUDA engine is forward-only this round: the loss VALUE is
-    available (validation); gradients are not."""
+    """Weighted denoising loss (diffusion.py:118-143).  Under `torch.no_grad()` / `eval()` the denoiser runs in the fused
+    sampling engine (validation); in `train()` mode with autograd on it runs the differentiable path of training.py."""
 
     def __init__(self, schedule: nn.Module, sigma_data: float = 1.0, loss_scale: float = 100.0):
         super().__init__()
@@ -131,7 +139,13 @@ class Diffusion(_Base):
         return torch.optim.Adam(self.parameters(), lr=1e-4)
 
     def training_step(self, batch: Example, batch_idx):
-        raise NotImplementedError("gecco_b200: the CUDA engine is forward-only; training is out of scope this round")
+        """diffusion.py:210-222: the loss of one batch, with an autograd graph when the module is in train() mode (see
+        training.Trainer for the whole step: backward, gradient all-reduce, fused Adam + EMA)."""
+        x, ctx = batch
+        loss = self.loss(self, x, ctx)
+        if hasattr(self, "log"):
+            self.log("train_loss", loss)
+        return loss
 
     @torch.no_grad()
     def validation_step(self, batch: Example, batch_idx):

@@ -498,3 +498,15 @@ def unpool_attention(q: Tensor, khv: Tensor, *, clouds: int, rows_per_cloud: int
         a.vt_scratch = vt.data_ptr()
     _abi.check(lib.gecco_unpool_attention(C.byref(a), _stream(q)))
     return out
+
+
+def adam_ema_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ema: Tensor | None, step: int, *, lr: float = 1e-4,
+                  betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
+                  ema_decay: float = 0.999) -> None:
+    """One fused Adam + weight-EMA update over flat fp32 buffers, in place (gecco_adam_ema_step; the reference's
+    torch.optim.Adam defaults, diffusion.py:207-208, and ema.py:187-194)."""
+    lib = _lib_for(p)
+    for t in (p, g, m, v) + ((ema,) if ema is not None else ()):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel() and t.device == p.device
+    _abi.check(lib.gecco_adam_ema_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(ema), p.numel(), int(step), float(lr), float(betas[0]),
+                                       float(betas[1]), float(eps), float(grad_scale), float(ema_decay), _stream(p)))

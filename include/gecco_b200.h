@@ -464,6 +464,18 @@ typedef struct gecco_upsample_step_args {
 int64_t gecco_upsample_workspace_bytes(const gecco_engine* e, int32_t clouds, int32_t seed_points, int32_t new_points);
 int gecco_upsample_step(gecco_engine* e, const gecco_upsample_step_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Training-step tail (BASELINE config 5): torch.optim.Adam (the reference's configure_optimizers, diffusion.py:207-208;
+ * defaults betas (0.9, 0.999), eps 1e-8, no weight decay) fused with the weight EMA of ema.py:187-194
+ * (ema = decay * ema + (1 - decay) * p_new) over FLAT fp32 buffers of n elements, one launch:
+ *   g' = grad_scale * g;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps);   ema (may be NULL) updated from the new p.
+ * `step` counts from 1.  All buffers 16-byte aligned.  The scalars are doubles so that 1 - beta and the bias corrections
+ * are formed exactly like torch forms them from Python floats before rounding to fp32.
+ * ------------------------------------------------------------------------ */
+int gecco_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int64_t step, double lr,
+                        double beta1, double beta2, double eps, double grad_scale, double ema_decay, void* stream);
+
 /* Per-kernel-class device timing of the engine (tracing aid; the reference has none).  Between
  * start and stop every engine launch on this thread is bracketed by CUDA events on its stream; stop synchronises
  * the device and returns, per class, the launch count, summed device time and the algorithmic FLOPs / bytes. */

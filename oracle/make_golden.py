@@ -348,8 +348,57 @@ def module_goldens():
     print("modules.pt", (OUT / "modules.pt").stat().st_size, {k: (v.pow(2).mean().sqrt().item() if torch.is_tensor(v) else None) for k, v in out.items()})
 
 
+def grad_goldens():
+    """tests/golden/grads_*.pt: the EDM training loss (diffusion.py:118-143, 210-222) and its GRADIENTS w.r.t. every
+    parameter, from the unmodified reference (fp32, CPU) on seeded draws: per-parameter gradient norm and a strided
+    sub-sample of every gradient.  Mode-dependent layers (torchvision's StochasticDepth inside ConvNeXt) are in eval mode."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    OUT.mkdir(parents=True, exist_ok=True)
+    common = dict(weight_seed=WEIGHT_SEED, feature_dim=synth.FEATURE_DIM, n_layers=synth.N_LAYERS, num_heads=synth.NUM_HEADS,
+                  num_inducers=synth.NUM_INDUCERS, torch=torch.__version__)
+    specs = [
+        dict(name="grads_uncond", kind="uncond", reparam="gaussian", **synth.UNCOND_REPARAM, sigma_max=165.0, B=2, N=1000),
+        dict(name="grads_cond_gaussian", kind="cond", reparam="gaussian", **synth.SHAPENET_VOL_REPARAM, sigma_max=165.0, B=2, N=1024,
+             K=synth.K_SHAPENET, image=137, convnext_seed=0, image_seed=123),
+    ]
+    for sp in specs:
+        kind, rp, B, N = sp["kind"], sp["reparam"], sp["B"], sp["N"]
+        if kind == "uncond":
+            model = build_reference(kind, rp, sp["mean"], sp["sigma"], sp["sigma_max"])
+            ctx = None
+        else:
+            model = build_reference_convnext(rp, sp["mean"], sp["sigma"], sp["sigma_max"], sp["convnext_seed"])
+            img = torch.rand(B, 3, sp["image"], sp["image"], generator=synth.gen(sp["image_seed"]))
+            ctx = Context3d(image=img, K=synth.camera(B, sp["K"]))
+        model.eval()
+        with torch.no_grad():
+            ex = model.reparam.diffusion_to_data(torch.randn(B, N, 3, generator=synth.gen(52)), ctx)
+        torch.manual_seed(53)
+        loss = model.loss(model, ex, ctx)
+        loss.backward()
+        torch.manual_seed(53)
+        u = torch.rand(B)
+        n = torch.randn_like(ex)
+        norms, subs = {}, {}
+        for k, p_ in model.named_parameters():
+            if p_.grad is None:
+                continue
+            g = p_.grad.detach().flatten()
+            norms[k] = g.double().norm().item()
+            stride = max(1, g.numel() // 256)
+            subs[k] = g[::stride].clone()
+        total = sum(v * v for v in norms.values()) ** 0.5
+        print(sp["name"], "loss", loss.item(), "params with grad", len(norms), "total grad norm", total)
+        recipe = {**common, **{k: v for k, v in sp.items() if k != "name"}, "ex_seed": 52, "loss_seed": 53}
+        torch.save(dict(recipe=recipe, loss=loss.detach(), loss_u=u, loss_noise_sub=n[:, ::64].contiguous(), grad_norm=norms,
+                        grad_sub=subs), OUT / (sp["name"] + ".pt"))
+        print((OUT / (sp["name"] + ".pt")).stat().st_size)
+
+
 if __name__ == "__main__":
-    if "--modules" in sys.argv:
+    if "--grads" in sys.argv:
+        grad_goldens()
+    elif "--modules" in sys.argv:
         module_goldens()
     elif "--bench-shape" in sys.argv:
         bench_shape()
