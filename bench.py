@@ -61,11 +61,17 @@ CONFIGS = {
             kind="cond", reparam="uvl", mean=[0.0, 0.0, 1.38], sigma=[0.56, 0.60, 0.49], sigma_max=180.0, clouds=8, image=256,
             K=[[1.2, 0.0, 0.5], [0.0, 1.2, 0.5], [0.0, 0.0, 1.0]],
             flop_per_cloud=NUM_STEPS * FLOP_COND + (NUM_STEPS * UPS_SUBSTEPS * 2 - UPS_SUBSTEPS) * FLOP_CACHED_16K),
+    5: dict(name="EDM training step (denoising loss, forward + backward, gradient all-reduce, fused Adam + EMA) on the config-2 model",
+            kind="cond", reparam="gaussian", mean=[0.0, 0.0, 1.0], sigma=[0.15, 0.15, 0.15], sigma_max=165.0, clouds=32, image=137,
+            K=[[1.0859, 0.0, 0.4964], [0.0, 1.0859, 0.4964], [0.0, 0.0, 1.0]], flop_per_cloud=3 * FLOP_COND),
 }
 
 
 def workload_text(c: dict, clouds: int) -> str:
     img = "" if c["image"] is None else f", synthetic 3x{c['image']}x{c['image']} images + cameras"
+    if c is CONFIGS[5]:
+        return (f"{c['name']}, {POINTS} points{img}, {clouds} clouds per GPU and step, bf16 GEMM operands / fp32 accumulation, "
+                f"master weights and optimiser state, random-init weights")
     if c is CONFIGS[4]:
         return (f"{c['name']}{img}, {clouds} clouds per GPU, {NUM_STEPS} steps x {UPS_SUBSTEPS} substeps "
                 f"({NUM_STEPS} full + {NUM_STEPS * UPS_SUBSTEPS * 2 - UPS_SUBSTEPS} cached evaluations), random-init weights")
@@ -170,7 +176,7 @@ KERNEL_OF_CLASS = {
     "unpool_attention": "unpool_tc_kernel (tcgen05): inducers -> points attention core",
     "inducer_chain": "inducer-side chain (out_proj, AdaGN, MLP, AdaGN, k/v in-projection)",
     "fold_adagn": "fold_adagn_fast_kernel: AdaGN folded into per-cloud projection weights",
-    "mlp_fused": "mlp_fused_kernel (tcgen05 cta_group::2): GEMM -> activation -> GEMM with the hidden tensor on chip",
+    "mlp_fused": "mlp_pair_kernel (tcgen05 cta_group::2): AdaGN -> GEMM -> Gaussian activation -> GEMM -> + residual, hidden row block parked in L2",
     "lookup": "lookup kernel (projective bilinear gather)", "head_edm_step": "head_kernel: output head + EDM sampler update",
 }
 
@@ -339,6 +345,112 @@ def run_own(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ config 5: training step
+def run_train(args):
+    """BASELINE config 5: one optimisation step = EDM loss forward + backward, bucketed gradient all-reduce (NCCL) overlapped
+    with backward, fused Adam + EMA; `value` with the batch resident, `e2e` from pinned host batches to the host loss."""
+    import torch.distributed as dist
+
+    import gecco_b200 as G
+    from gecco_b200 import training as T
+
+    cfg = CONFIGS[5]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    model = build_model(device, cfg)
+    B = args.clouds or cfg["clouds"]
+    g = torch.Generator("cpu").manual_seed(123 + rank)
+    images_h = torch.rand(B, 3, cfg["image"], cfg["image"], generator=g).pin_memory()
+    K_h = torch.tensor(cfg["K"]).expand(B, 3, 3).contiguous().pin_memory()
+    ctx_d = G.Context3d(image=images_h.to(device), K=K_h.to(device))
+    data_d = model.reparam.diffusion_to_data(torch.randn(B, POINTS, 3, generator=g).to(device), ctx_d).float()
+    data_h = data_d.cpu().pin_memory()
+    trainer = T.Trainer(model, lr=1e-4, graph=os.environ.get("GECCO_TRAIN_GRAPH", "1") != "0")
+    torch.manual_seed(1 + rank)
+
+    def step_resident():
+        return trainer.step((data_d, ctx_d))
+
+    def step_e2e():
+        ctx = G.Context3d(image=images_h.to(device, non_blocking=True), K=K_h.to(device, non_blocking=True))
+        return trainer.step((data_h.to(device, non_blocking=True), ctx)).item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return ms.item(), out
+
+    for _ in range(args.warmup):
+        loss = step_resident()
+    assert torch.isfinite(loss), "non-finite training loss"
+    from gecco_b200 import engine as E
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    E.launch_count(reset=True)
+    ms, loss = timed(step_resident, args.steps)
+    launches = E.launch_count(reset=True)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clk = clocks.stop() if clocks else None
+    mem_gb = torch.cuda.max_memory_allocated(device) / 2**30
+    # the library arm: the same step with every projection on torch's own kernels (GECCO_TRAIN_TC=0)
+    lib_ms = None
+    if world == 1 and not args.no_cpu_baseline:
+        os.environ["GECCO_TRAIN_TC"] = "0"
+        try:
+            lib_trainer = T.Trainer(model, lr=1e-4, graph=trainer.graph_mode)  # its own capture, with the library projections
+            step_lib = lambda: lib_trainer.step((data_d, ctx_d))
+            for _ in range(2):
+                step_lib()
+            lib_ms, _ = timed(step_lib, args.steps)
+        finally:
+            os.environ.pop("GECCO_TRAIN_TC", None)
+    if rank == 0:
+        pk = peaks()
+        clouds = world * B * args.steps
+        tf = B * cfg["flop_per_cloud"] * args.steps / (ms * 1e-3) / 1e12
+        line = {
+            "metric": "training clouds/sec (2048 pts, EDM loss fwd+bwd, gradient all-reduce, Adam+EMA)", "value": clouds / (ms * 1e-3),
+            "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_text(cfg, B), "baseline_config": 5, "clouds_per_gpu": B, "points": POINTS,
+                       "l2": "no flush needed: one step streams tens of GB of activations per GPU",
+                       "parallelism": f"dp{world} (batch sharded on dim 0; gradient all-reduce in "
+                                      f"{len(trainer.reducer.buckets)} buckets overlapped with backward)"},
+            "e2e": {"value": clouds / (ms_e2e * 1e-3), "unit": "clouds/s",
+                    "h2d_bytes_per_step": images_h.numel() * 4 + K_h.numel() * 4 + data_h.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "cuda_graph": "replayed" if trainer.graph_mode else "off (eager autograd)", "loss": float(loss), "peak_memory_gb": mem_gb, "clocks": clk,
+            "parameters": trainer.state.numel,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                         "traffic": None, "kernel": "whole training step (3 x the forward FLOPs of BASELINE.md §3 per cloud)",
+                         "peak_source": pk["source"]},
+            "library_baseline": None if lib_ms is None else {
+                "value": clouds / (lib_ms * 1e-3), "unit": "clouds/s", "kind": "the same step with every projection on torch / cuBLAS "
+                "kernels (bf16 autocast-equivalent operands), same process", "ms_per_step": lib_ms / args.steps},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ reference arms
 def _oracle_setup(cfg: dict, B: int, device="cpu"):
     from oracle import gecco_oracle as O
@@ -481,6 +593,8 @@ def main():
                "127.0.0.1", "--master-port", "29531", __file__, "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
                str(args.warmup), "--config", str(args.config)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
         raise SystemExit(subprocess.call(cmd))
+    if args.config == 5:
+        return run_train(args)
     run_own(args)
 
 

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 from typing import Iterable, Sequence
 
 import torch
@@ -45,7 +46,6 @@ class TCLinear(torch.autograd.Function):
         y, _ = ops.gemm(xb, wb, bias=None if bias is None else bias.detach().float().contiguous(), out_f32=True)
         ctx.save_for_backward(xb, wb)
         ctx.has_bias = bias is not None
-        ctx.needs = (x.requires_grad, weight.requires_grad)
         return y
 
     @staticmethod
@@ -53,12 +53,12 @@ class TCLinear(torch.autograd.Function):
         xb, wb = ctx.saved_tensors
         dyb = dy.to(torch.bfloat16).contiguous()
         dx = dw = db = None
-        if ctx.needs[0]:
+        if ctx.needs_input_grad[0]:
             # dX [M, K] = dY [M, N] . W [N, K]: the same kernel with W^T as its (row-major [K, N]) weight operand
             dx, _ = ops.gemm(dyb, wb.t().contiguous(), out_f32=True)
-        if ctx.needs[1]:
+        if ctx.needs_input_grad[1]:
             dw = _mm_f32(dyb.t(), xb)
-        if ctx.has_bias:
+        if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(dim=0)
         return dx, dw, db
 
@@ -74,9 +74,12 @@ def _mm_f32(a: Tensor, b: Tensor) -> Tensor:
 def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None) -> Tensor:
     """F.linear on [..., K]; through the tcgen05 GEMM when the shape allows (K, N multiples of 8, CUDA)."""
     K, N = lin_w.shape[1], lin_w.shape[0]
-    if x.is_cuda and K % 8 == 0 and N % 8 == 0 and x.numel() > 0:
+    if x.is_cuda and K % 8 == 0 and N % 8 == 0 and x.numel() > 0 and os.environ.get("GECCO_TRAIN_TC", "1") != "0":
         y = TCLinear.apply(x.reshape(-1, K), lin_w, lin_b)
         return y.view(*x.shape[:-1], N)
+    if x.is_cuda:  # library arm of the A/B (GECCO_TRAIN_TC=0) and odd shapes: cuBLAS with the same bf16 operands
+        y = F.linear(x.to(torch.bfloat16), lin_w.to(torch.bfloat16), None if lin_b is None else lin_b.to(torch.bfloat16))
+        return y.float()
     return F.linear(x, lin_w, lin_b)
 
 
@@ -273,7 +276,7 @@ class GradReducer:
     parameter backwards since backward produces gradients roughly in reverse order."""
 
     def __init__(self, params: Sequence[nn.Parameter], offsets: Sequence[int], flat_grad: Tensor, bucket_bytes: int = 64 << 20,
-                 group=None):
+                 group=None, hooks: bool = True):
         self.flat = flat_grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -297,7 +300,7 @@ class GradReducer:
         self.launched = [False] * len(self.buckets)
         self.works: list = []
         self.handles = []
-        if self.world > 1:
+        if self.world > 1 and hooks:  # hooks off: finish() reduces every bucket (after a CUDA-graph replay of backward)
             for i, p in enumerate(params):
                 self.handles.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
 
@@ -336,28 +339,76 @@ class GradReducer:
 
 class Trainer:
     """forward + backward + gradient all-reduce + fused Adam / EMA for a `Diffusion` model (the reference runs the same
-    sequence under Lightning with torch.optim.Adam(lr=1e-4) and its EMA callback)."""
+    sequence under Lightning with torch.optim.Adam(lr=1e-4) and its EMA callback).
+
+    graph=False: eager autograd; bucket all-reduces start from gradient hooks while backward is still running.
+    graph=True : forward + backward of a fixed batch shape are captured ONCE as a CUDA graph and replayed on static input
+                 buffers (the eager step is host-bound: thousands of small autograd launches); the flat gradient buffer
+                 is then all-reduced bucket by bucket and the optimiser kernel follows.  Noise levels and noise are drawn
+                 inside the graph from torch's graph-safe CUDA generator, so every replay sees fresh draws."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-4, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 ema_decay: float = 0.999, bucket_mb: int = 64, group=None):
+                 ema_decay: float = 0.999, bucket_mb: int = 64, group=None, graph: bool = False):
         self.model = model
         self.lr, self.betas, self.eps, self.ema_decay = lr, betas, eps, ema_decay
         self.state = FlatState(model.parameters(), with_ema=ema_decay is not None)
-        self.reducer = GradReducer(self.state.params, self.state.offsets, self.state.g, bucket_mb << 20, group)
+        self.graph_mode = graph
+        self.reducer = GradReducer(self.state.params, self.state.offsets, self.state.g, bucket_mb << 20, group, hooks=not graph)
         self.steps = 0
+        self._graph = None
+        self._static = None
 
     def step(self, batch) -> Tensor:
         """One optimisation step on `batch` = (data [B, N, 3], Context3d | None); returns the (detached) loss."""
         self.model.train()
-        self.state.zero_grad()
-        loss = self.model.training_step(batch, self.steps)
-        loss.backward()
+        if self.graph_mode:
+            loss = self._graphed_forward_backward(batch)
+        else:
+            self.state.zero_grad()
+            loss = self.model.training_step(batch, self.steps)
+            loss.backward()
         scale = self.reducer.finish()
         self.steps += 1
         ops.adam_ema_step(self.state.p, self.state.g, self.state.m, self.state.v, self.state.ema, self.steps, lr=self.lr,
                           betas=self.betas, eps=self.eps, grad_scale=scale,
                           ema_decay=self.ema_decay if self.ema_decay is not None else 0.0)
         return loss.detach()
+
+    # ---- CUDA-graph path
+    @staticmethod
+    def _tensors(batch):
+        data, ctx = batch
+        return [data] + ([] if ctx is None else [ctx.image, ctx.K])
+
+    def _graphed_forward_backward(self, batch) -> Tensor:
+        ts = self._tensors(batch)
+        key = tuple((tuple(t.shape), t.dtype) for t in ts)
+        if self._graph is None or self._static["key"] != key:
+            self._capture(batch, key)
+        for dst, src in zip(self._static["tensors"], ts):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static["loss"].clone()
+
+    def _capture(self, batch, key) -> None:
+        data, ctx = batch
+        s_data = data.clone()
+        s_ctx = None if ctx is None else type(ctx)(image=ctx.image.clone(), K=ctx.K.clone())
+        static_batch = (s_data, s_ctx)
+        side = torch.cuda.Stream(device=data.device)
+        side.wait_stream(torch.cuda.current_stream(data.device))
+        with torch.cuda.stream(side):  # warm-up outside the capture (lazy initialisations, cuDNN plans, tensor-map cache)
+            for _ in range(2):
+                self.state.zero_grad()
+                self.model.training_step(static_batch, 0).backward()
+        torch.cuda.current_stream(data.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.state.g.zero_()
+            loss = self.model.training_step(static_batch, 0)
+            loss.backward()
+        self._static = dict(key=key, tensors=self._tensors(static_batch), loss=loss.detach())
 
     @contextlib.contextmanager
     def ema_weights(self):

@@ -193,3 +193,37 @@ def test_trainer_reduces_loss(cuda):
     with torch.no_grad():
         s = model.sample_stochastic((2, 256, 3), None, rng=torch.Generator(cuda).manual_seed(0), num_steps=4)
     assert torch.isfinite(s).all()
+
+
+def test_graphed_step_matches_eager(cuda):
+    """The CUDA-graph replay of forward + backward produces the eager step's loss and gradients (fixed draws), keeps
+    working when the batch changes, and trains."""
+    import gecco_b200 as G
+    from gecco_b200.training import Trainer
+
+    class FixedDrawLoss(G.EDMLoss):  # the reference loss with its two draws replaced by stored device tensors
+        def forward(self, net, examples, context):
+            ex_diff = net.reparam.data_to_diffusion(examples, context)
+            sigma = self.fixed_sigma
+            weight = (sigma**2 + self.sigma_data**2) / ((sigma * self.sigma_data) ** 2)
+            D = net(ex_diff + self.fixed_noise * sigma, sigma, context)
+            return (self.loss_scale * weight * (D - ex_diff) ** 2).mean()
+
+    results = []
+    for graph in (False, True):
+        g, r, model, ctx, ex = _setup("grads_uncond", cuda)
+        loss_mod = FixedDrawLoss(schedule=model.loss.schedule)
+        loss_mod.fixed_sigma = torch.tensor([0.4, 6.0], device=cuda).reshape(-1, 1, 1)
+        loss_mod.fixed_noise = torch.randn(r["B"], r["N"], 3, generator=synth.gen(4)).to(cuda)
+        model.loss = loss_mod
+        tr = Trainer(model, lr=5e-5, graph=graph)
+        l0 = tr.step((ex, ctx))
+        g0 = tr.state.g.clone()
+        ex2 = ex.flip(0).contiguous()  # a different batch of the same shape goes through the static buffers
+        l1 = tr.step((ex2, ctx))
+        results.append((l0.item(), g0, l1.item(), tr.state.p.clone()))
+    (a0, ga, a1, pa), (b0, gb, b1, pb) = results
+    print(f"eager losses {a0:.6g} {a1:.6g}; graphed {b0:.6g} {b1:.6g}")
+    assert abs(a0 - b0) <= 1e-5 * abs(a0) and abs(a1 - b1) <= 1e-3 * abs(a1)
+    assert rms(ga - gb) <= 1e-4 * rms(ga)
+    assert rms(pa - pb) <= 1e-4 * rms(pa)
