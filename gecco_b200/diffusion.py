@@ -283,6 +283,81 @@ class Diffusion(_Base):
                     x += (math.sqrt(max(s_cur**2 - s_next**2, 0.0)) * randn(x.shape)).to(torch.float64)
         return self.reparam.diffusion_to_data(x, context)[:, :M]
 
+    def log_likelihood(self, data: Tensor, context: Context3d | None, rng: torch.Generator = None,
+                       n_log_det_jac_samples: int = 1, return_details: bool = False, noise: Tensor | None = None, **kwargs):
+        """log p(data) per cloud [B] through the probability-flow ODE (gecco-jax `evaluate_logp`,
+        models/diffusion.py:444-541, with gecco-torch's sigma(t) = t, scale = 1 schedule): the data (in diffusion space) is
+        integrated from sigma_min up to sigma_max with Heun's method over the reversed EDM noise levels; next to it the
+        divergence of dx/dt = (x - D(x; t)) / t, estimated by Hutchinson's estimator with Rademacher probes eps,
+        eps . grad_x(f(x) . eps) (`trace_jac_estimator`, :175-193; the same probes at every level, like the reference's single
+        noise key).  log p = log N(latent; 0, sigma_max) + integral of the divergence + log |det d diffusion / d data|.
+
+        Every evaluation is one forward + one input-gradient pass of the differentiable network (training.py, input-gradient
+        mode): projections and their dX products on the tcgen05 GEMM, no weight gradients.  `noise`
+        ([n_samples, B, N, 3], entries +-1) overrides the probes drawn from `rng`."""
+        from . import training
+
+        kw = {**self.sampler_kwargs, **kwargs}
+        num_steps = kw["num_steps"]
+        device, dtype = self.example_param.device, self.example_param.dtype
+        data = data.to(device=device, dtype=dtype)
+        if noise is None:
+            if rng is None:
+                rng = torch.Generator(device).manual_seed(42)
+            shape = (n_log_det_jac_samples, *data.shape)
+            noise = (torch.randint(0, 2, shape, generator=rng, device=rng.device) * 2 - 1).to(device=device, dtype=dtype)
+        else:
+            noise = noise.to(device=device, dtype=dtype)
+        net, _ = self._network()
+        with torch.no_grad():
+            post_context = self.conditioner(context)
+        ts = self._t_steps_host(num_steps, kw["sigma_max"], kw["sigma_min"], kw["rho"])[:-1].flip(0).tolist()
+
+        # log |det J| of data -> diffusion, per cloud: points are independent, so the 3 x 3 blocks come from three passes
+        with torch.enable_grad():
+            d_in = data.detach().clone().requires_grad_(True)
+            x0 = training.reparam_to_diffusion(self.reparam, d_in, context)
+            if x0 is d_in:
+                ladj = torch.zeros(data.shape[0], device=device, dtype=torch.float64)
+            else:
+                rows = [torch.autograd.grad(x0[..., i].sum(), d_in, retain_graph=i < 2)[0] for i in range(3)]
+                ladj = torch.linalg.slogdet(torch.stack(rows, dim=-2).double())[1].sum(dim=1)
+            x0 = x0.detach()
+
+        def f_and_div(x: Tensor, t: float):
+            """dx/dt at noise level t and the Hutchinson estimate of its divergence per cloud."""
+            with torch.enable_grad(), training.input_gradients():
+                xin = x.to(dtype).detach().requires_grad_(True)
+                sigma = torch.full((x.shape[0],), t, device=device, dtype=dtype)
+                D = training.precond_forward(self.backbone, xin, sigma, context, post_context)
+                f = (xin - D) / t
+                div = torch.zeros(x.shape[0], device=device, dtype=torch.float64)
+                for s in range(noise.shape[0]):
+                    g = torch.autograd.grad((f * noise[s]).sum(), xin, retain_graph=s < noise.shape[0] - 1)[0]
+                    div += (g * noise[s]).double().flatten(1).sum(1)
+            return f.detach().double(), div / noise.shape[0]
+
+        x = x0.double()
+        delta = torch.zeros(data.shape[0], device=device, dtype=torch.float64)
+        traj = [x] if return_details else None
+        f0, d0 = f_and_div(x, ts[0])
+        for i in range(len(ts) - 1):
+            dt = ts[i + 1] - ts[i]
+            f1, d1 = f_and_div(x + dt * f0, ts[i + 1])
+            x = x + 0.5 * dt * (f0 + f1)
+            delta = delta + 0.5 * dt * (d0 + d1)
+            if return_details:
+                traj.append(x)
+            if i < len(ts) - 2:
+                f0, d0 = f_and_div(x, ts[i + 1])
+        smax = ts[-1]
+        prior = (-0.5 * (x / smax) ** 2 - math.log(smax) - 0.5 * math.log(2 * math.pi)).flatten(1).sum(1)
+        logp = prior + delta + ladj
+        if not return_details:
+            return logp
+        return dict(logp=logp, prior_logp=prior, delta_reparam=ladj, delta_jacobian=delta, latent=x,
+                    trajectory_diff=torch.stack(traj))
+
     def _network(self):
         bb = self.backbone
         if not isinstance(bb, EDMPrecond):

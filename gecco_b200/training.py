@@ -71,9 +71,26 @@ def _mm_f32(a: Tensor, b: Tensor) -> Tensor:
         return torch.mm(a, b).float()
 
 
+# Input-gradient mode (Diffusion.log_likelihood): gradients flow to the network INPUT only -- weights are detached (no dW
+# products) and the projective lookup becomes differentiable in the sample positions.
+_INPUT_GRAD_ONLY = False
+
+
+@contextlib.contextmanager
+def input_gradients():
+    global _INPUT_GRAD_ONLY
+    prev, _INPUT_GRAD_ONLY = _INPUT_GRAD_ONLY, True
+    try:
+        yield
+    finally:
+        _INPUT_GRAD_ONLY = prev
+
+
 def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None) -> Tensor:
     """F.linear on [..., K]; through the tcgen05 GEMM when the shape allows (K, N multiples of 8, CUDA)."""
     K, N = lin_w.shape[1], lin_w.shape[0]
+    if _INPUT_GRAD_ONLY:
+        lin_w, lin_b = lin_w.detach(), None if lin_b is None else lin_b.detach()
     if x.is_cuda and K % 8 == 0 and N % 8 == 0 and x.numel() > 0 and os.environ.get("GECCO_TRAIN_TC", "1") != "0":
         y = TCLinear.apply(x.reshape(-1, K), lin_w, lin_b)
         return y.view(*x.shape[:-1], N)
@@ -177,9 +194,51 @@ def _project(points: Tensor, K: Tensor) -> Tensor:
     return torch.stack([xy[..., 0] * Kb[..., 0, 0] + Kb[..., 0, 2], xy[..., 1] * Kb[..., 1, 1] + Kb[..., 1, 2]], dim=-1)
 
 
+def reparam_to_data(reparam, diff: Tensor, ctx) -> Tensor:
+    """`Reparam.diffusion_to_data` (reparam.py:31-40, 62-64, 191-201) as differentiable torch expressions (the product's
+    `gecco_reparam` kernel has no backward)."""
+    from .reparam import GaussianReparam, NoReparam, UVLReparam
+
+    if isinstance(reparam, NoReparam):
+        return diff
+    if isinstance(reparam, GaussianReparam):
+        return diff * reparam.sigma.to(diff) + reparam.mean.to(diff)
+    if isinstance(reparam, UVLReparam):
+        uvl = diff * reparam.uvl_std.to(diff) + reparam.uvl_mean.to(diff)
+        K = ctx.K.unsqueeze(1).to(diff)
+        hw = (torch.tanh(uvl[..., :2]) * reparam.logit_scale + 1.0) / 2
+        x = (hw[..., 0] - K[..., 0, 2]) / K[..., 0, 0]
+        y = (hw[..., 1] - K[..., 1, 2]) / K[..., 1, 1]
+        ray = F.normalize(torch.stack([x, y, torch.ones_like(x)], dim=-1), dim=-1, p=2.0)
+        return ray * torch.exp(uvl[..., 2:])
+    raise TypeError(f"gecco_b200.training: unsupported reparametrisation {type(reparam).__name__}")
+
+
+def reparam_to_diffusion(reparam, data: Tensor, ctx) -> Tensor:
+    """`Reparam.data_to_diffusion` (reparam.py:58-60, 178-189), differentiable."""
+    from .reparam import GaussianReparam, NoReparam, UVLReparam
+
+    if isinstance(reparam, NoReparam):
+        return data
+    if isinstance(reparam, GaussianReparam):
+        return (data - reparam.mean.to(data)) / reparam.sigma.to(data)
+    if isinstance(reparam, UVLReparam):
+        hw = _project(data, ctx.K.to(data))
+        real = torch.arctanh((2 * hw - 1.0) / reparam.logit_scale)
+        uvl = torch.cat([real, torch.log(torch.linalg.norm(data, dim=-1, keepdim=True))], dim=-1)
+        return (uvl - reparam.uvl_mean.to(data)) / reparam.uvl_std.to(data)
+    raise TypeError(f"gecco_b200.training: unsupported reparametrisation {type(reparam).__name__}")
+
+
 def extract_image_features(net, geometry_diffusion: Tensor, features: Sequence[Tensor], raw_ctx) -> Tensor:
-    """models/ray.py:64-87.  The sample positions carry no gradient (the network input is data + noise); the feature
-    maps do (the conditioner trains), which is why this is F.grid_sample and not the sampling path's gather kernel."""
+    """models/ray.py:64-87.  While training the sample positions carry no gradient (the network input is data + noise);
+    the feature maps do (the conditioner trains), which is why this is F.grid_sample and not the sampling path's gather
+    kernel.  In input-gradient mode (log-likelihood) the positions are differentiable too."""
+    if _INPUT_GRAD_ONLY:
+        data = reparam_to_data(net.reparam, geometry_diffusion.float(), raw_ctx)
+        grid = (_project(data, raw_ctx.K.float()) * 2 - 1).unsqueeze(2)
+        looks = [F.grid_sample(f.detach().float(), grid, align_corners=False)[..., 0].transpose(1, 2) for f in features]
+        return torch.cat(looks, dim=-1)
     with torch.no_grad():
         data = net.reparam.diffusion_to_data(geometry_diffusion.detach().float().contiguous(), raw_ctx)
         grid = (_project(data, raw_ctx.K.float()) * 2 - 1).unsqueeze(2)  # [B, N, 1, 2]

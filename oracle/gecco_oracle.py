@@ -360,3 +360,47 @@ def edm_loss(cfg: OracleConfig, sd: dict, examples: Tensor, u: Tensor, noise: Te
     weight = (sigma**2 + cfg.sigma_data**2) / ((sigma * cfg.sigma_data) ** 2)  # :138
     D = denoise(cfg, sd, ex_diff + noise * sigma, sigma, features, K)
     return (loss_scale * weight * (D - ex_diff) ** 2).mean()  # :141-142
+
+
+# gecco-jax models/diffusion.py:444-541 (`evaluate_logp`) with `trace_jac_estimator` (:175-193) and `_dx_dt` (:309-332),
+# restated with the EDM schedule sigma(t) = t, scale = 1 of gecco-torch: Heun's method (diffrax `Heun` under `StepTo`, no
+# FSAL: the derivative is re-evaluated at the start of every step) over the reversed noise levels from sigma_min to
+# sigma_max on the pair (x, accumulated divergence); divergence = mean over the Rademacher probes `noise`
+# [S, B, N, 3] of eps . grad_x(f(x) . eps).  The log-abs-det of data -> diffusion follows `ReparamDiagonalBlockJacrev`
+# (models/reparam.py:27-48): per-point 3 x 3 Jacobians by reverse mode, slogdet, summed per cloud.  gecco-jax cannot run in
+# the build container, so this restatement is NOT pinned by reference outputs; tests/test_oracle.py checks it against the
+# closed-form likelihood of a linear denoiser instead.
+def log_likelihood(cfg: OracleConfig, sd: dict, data: Tensor, noise: Tensor, features=None, K=None, denoise_fn=None, **kw):
+    k = {**cfg.sampler, "sigma_max": cfg.sigma_max, **kw}
+    ts = t_steps(k["num_steps"], k["sigma_max"], k["sigma_min"], k["rho"])[:-1].flip(0).tolist()
+    if denoise_fn is None:
+        denoise_fn = lambda x, sig: denoise(cfg, sd, x, sig, features, K)
+    B = data.shape[0]
+    d_in = data.detach().clone().float().requires_grad_(True)
+    x0 = data_to_diffusion(cfg, sd, d_in, K)
+    if cfg.reparam == "none":
+        ladj = torch.zeros(B, dtype=torch.float64)
+    else:
+        rows = [torch.autograd.grad(x0[..., i].sum(), d_in, retain_graph=True)[0] for i in range(3)]
+        ladj = torch.linalg.slogdet(torch.stack(rows, dim=-2).double())[1].sum(dim=1)
+
+    def f_and_div(x: Tensor, t: float):
+        xin = x.float().detach().requires_grad_(True)
+        f = (xin - denoise_fn(xin, torch.full((B,), t, dtype=torch.float32))) / t
+        div = torch.zeros(B, dtype=torch.float64)
+        for s in range(noise.shape[0]):
+            g = torch.autograd.grad((f * noise[s]).sum(), xin, retain_graph=True)[0]
+            div += (g * noise[s]).double().flatten(1).sum(1)
+        return f.detach().double(), div / noise.shape[0]
+
+    x = x0.detach().double()
+    delta = torch.zeros(B, dtype=torch.float64)
+    for i in range(len(ts) - 1):
+        dt = ts[i + 1] - ts[i]
+        f0, d0 = f_and_div(x, ts[i])
+        f1, d1 = f_and_div(x + dt * f0, ts[i + 1])
+        x = x + 0.5 * dt * (f0 + f1)
+        delta = delta + 0.5 * dt * (d0 + d1)
+    smax = ts[-1]
+    prior = (-0.5 * (x / smax) ** 2 - math.log(smax) - 0.5 * math.log(2 * math.pi)).flatten(1).sum(1)
+    return dict(logp=prior + delta + ladj, prior_logp=prior, delta_jacobian=delta, delta_reparam=ladj, latent=x)

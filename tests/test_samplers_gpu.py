@@ -62,3 +62,28 @@ def test_inpaint_matches_oracle(cuda):
     e = rms(to_diff(got) - to_diff(ref)) / rms(to_diff(ref))
     print("inpaint rel rms (diffusion space)", e)
     assert got.shape == (B, M, 3) and got.dtype == torch.float64 and e < 1e-2
+
+
+@pytest.mark.parametrize("kind", ["uncond", "cond"])
+def test_log_likelihood_matches_oracle(cuda, kind):
+    """`Diffusion.log_likelihood` (gecco-jax `evaluate_logp`, models/diffusion.py:444-541) on the tcgen05 path (forward and
+    input-gradient products in bf16) against the fp32 CPU oracle with the same Rademacher probes."""
+    import gecco_b200 as G
+
+    B, N, steps = 2, 384, 6
+    feats = synth.synth_features(B, (34, 17, 8), 21) if kind == "cond" else None
+    model, sd, rp = _model(cuda, kind, feats)
+    K = synth.camera(B, synth.K_SHAPENET) if kind == "cond" else None
+    ctx = G.Context3d(image=torch.zeros(B, 3, 8, 8, device=cuda), K=K.to(cuda)) if kind == "cond" else None
+    cfg = O.OracleConfig(kind=kind, reparam="gaussian", sigma_max=165.0)
+    data = O.diffusion_to_data(cfg, sd, torch.randn(B, N, 3, generator=synth.gen(2)) * 0.8, K)
+    noise = (torch.randint(0, 2, (2, B, N, 3), generator=synth.gen(3)) * 2 - 1).float()
+    ref = O.log_likelihood(cfg, sd, data, noise, feats, K, num_steps=steps)
+    got = model.log_likelihood(data.to(cuda), ctx, noise=noise.to(cuda), num_steps=steps, return_details=True)
+    rel = lambda k: ((got[k].cpu() - ref[k]).abs() / ref[k].abs().clamp_min(1.0)).max().item()
+    print("log-likelihood", kind, {k: rel(k) for k in ("prior_logp", "delta_jacobian", "delta_reparam", "logp")},
+          "latent", rms(got["latent"].cpu() - ref["latent"]) / rms(ref["latent"]))
+    assert got["logp"].shape == (B,) and got["logp"].dtype == torch.float64
+    assert rel("delta_reparam") < 1e-5
+    assert rms(got["latent"].cpu() - ref["latent"]) / rms(ref["latent"]) < 1e-2
+    assert rel("prior_logp") < 1e-2 and rel("delta_jacobian") < 2e-2 and rel("logp") < 2e-2
