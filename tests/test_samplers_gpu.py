@@ -86,4 +86,5 @@ def test_log_likelihood_matches_oracle(cuda, kind):
     assert got["logp"].shape == (B,) and got["logp"].dtype == torch.float64
     assert rel("delta_reparam") < 1e-5
     assert rms(got["latent"].cpu() - ref["latent"]) / rms(ref["latent"]) < 1e-2
-    assert rel("prior_logp") < 1e-2 and rel("delta_jacobian") < 2e-2 and rel("logp") < 2e-2
+    # measured on B200: prior 1.6e-5 / 1.6e-6, divergence integral 4e-5 / 9.4e-4, log p 6e-5 / 2.9e-3 (uncond / cond)
+    assert rel("prior_logp") < 1e-3 and rel("delta_jacobian") < 5e-3 and rel("logp") < 1e-2
