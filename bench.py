@@ -411,10 +411,13 @@ def run_train(args):
     ms_e2e, _ = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
     mem_gb = torch.cuda.max_memory_allocated(device) / 2**30
-    # the library arm: the same step with every projection on torch's own kernels (GECCO_TRAIN_TC=0)
+    # the library arm: the same step with every projection on torch's own kernels (GECCO_TRAIN_TC=0) and the normalisations /
+    # activations through torch's own autograd ops (GECCO_TRAIN_FUSED=0)
     lib_ms = None
     if world == 1 and not args.no_cpu_baseline:
+        prev_fused = os.environ.get("GECCO_TRAIN_FUSED")
         os.environ["GECCO_TRAIN_TC"] = "0"
+        os.environ["GECCO_TRAIN_FUSED"] = "0"
         try:
             lib_trainer = T.Trainer(model, lr=1e-4, graph=trainer.graph_mode)  # its own capture, with the library projections
             step_lib = lambda: lib_trainer.step((data_d, ctx_d))
@@ -423,6 +426,9 @@ def run_train(args):
             lib_ms, _ = timed(step_lib, args.steps)
         finally:
             os.environ.pop("GECCO_TRAIN_TC", None)
+            os.environ.pop("GECCO_TRAIN_FUSED", None)
+            if prev_fused is not None:
+                os.environ["GECCO_TRAIN_FUSED"] = prev_fused
     if rank == 0:
         pk = peaks()
         clouds = world * B * args.steps

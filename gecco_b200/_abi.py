@@ -289,6 +289,15 @@ def load() -> C.CDLL:
     lib.gecco_graph_status.argtypes = [C.c_void_p]
     lib.gecco_adam_ema_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,
                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.gecco_train_gauss_act_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.gecco_train_gauss_act_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.gecco_train_affine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p]
+    lib.gecco_train_gauss_act_bwd_parts.argtypes = [C.c_int64]
+    lib.gecco_train_gauss_act_bwd_parts.restype = C.c_int64
+    lib.gecco_train_colsum2_parts.argtypes = [C.c_int32, C.c_int32]
+    lib.gecco_train_colsum2_parts.restype = C.c_int32
+    lib.gecco_train_colsum2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.gecco_graph_status.restype = C.c_int
     _lib = lib
     return lib

@@ -510,3 +510,46 @@ def adam_ema_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, ema: Tensor | None
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel() and t.device == p.device
     _abi.check(lib.gecco_adam_ema_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(ema), p.numel(), int(step), float(lr), float(betas[0]),
                                        float(betas[1]), float(eps), float(grad_scale), float(ema_decay), _stream(p)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training-path element-wise kernels (csrc/train_ops.cu)
+def _f32c(t: Tensor) -> Tensor:
+    assert t.dtype == torch.float32 and t.is_contiguous(), "fp32 contiguous tensor expected"
+    return t
+
+
+def train_gauss_act_fwd(x: Tensor, alpha: Tensor, normalized: bool = True) -> Tensor:
+    lib = _lib_for(x)
+    y = torch.empty_like(_f32c(x))
+    _abi.check(lib.gecco_train_gauss_act_fwd(_ptr(x), _ptr(_f32c(alpha)), _ptr(y), x.numel(), int(normalized), _stream(x)))
+    return y
+
+
+def train_gauss_act_bwd(x: Tensor, dy: Tensor, alpha: Tensor, normalized: bool = True) -> tuple[Tensor, Tensor]:
+    lib = _lib_for(x)
+    dx = torch.empty_like(_f32c(x))
+    parts = torch.empty((max(1, int(lib.gecco_train_gauss_act_bwd_parts(x.numel()))),), device=x.device, dtype=torch.float32)
+    _abi.check(lib.gecco_train_gauss_act_bwd(_ptr(x), _ptr(_f32c(dy)), _ptr(_f32c(alpha)), _ptr(dx), _ptr(parts), x.numel(),
+                                             int(normalized), _stream(x)))
+    return dx, parts.sum() if x.numel() else parts.sum() * 0
+
+
+def train_affine(u: Tensor, w: Tensor | None, p: Tensor, q: Tensor | None, r: Tensor) -> Tensor:
+    """out[b,n,c] = p[b,c] u + (q[b,c] w) + r[b,c] for u (and w) [B, N, C]; p, q, r [B, C]."""
+    lib = _lib_for(u)
+    B, N, Cc = u.shape
+    out = torch.empty_like(_f32c(u))
+    _abi.check(lib.gecco_train_affine(_ptr(u), _ptr(None if w is None else _f32c(w)), _ptr(_f32c(p)),
+                                      _ptr(None if q is None else _f32c(q)), _ptr(_f32c(r)), _ptr(out), B, N, Cc, _stream(u)))
+    return out
+
+
+def train_colsum2(dy: Tensor, x: Tensor) -> Tensor:
+    """[B, C, 2]: sum over the rows of dy and of dy * x."""
+    lib = _lib_for(x)
+    B, N, Cc = x.shape
+    parts = int(lib.gecco_train_colsum2_parts(N, Cc))
+    out = torch.empty((B, max(parts, 1), Cc, 2), device=x.device, dtype=torch.float32)
+    _abi.check(lib.gecco_train_colsum2(_ptr(_f32c(dy)), _ptr(_f32c(x)), _ptr(out), B, N, Cc, _stream(x)))
+    return out.sum(dim=1)

@@ -102,16 +102,92 @@ def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None) -> Tensor:
 
 # ----------------------------------------------------------------------------------------------------------------------
 # The network, differentiable (same arithmetic as the engine; citations are the reference's)
+def _fused() -> bool:
+    """GECCO_TRAIN_FUSED=0: normalisation and activation through torch's own ops (A/B arm, and the CPU path of the tests)."""
+    return os.environ.get("GECCO_TRAIN_FUSED", "1") != "0"
+
+
+class GroupAffineNorm(torch.autograd.Function):
+    """y[b,n,c] = gamma[b,c] * xhat[b,n,c] + beta[b,c], xhat = group normalisation of x over (rows x channels-in-group)
+    per cloud (nn.GroupNorm statistics: biased variance, eps inside the root).  Forward: `gecco_group_stats` (fp64 sums)
+    + one `gecco_train_affine` pass; backward: one `gecco_train_colsum2` reduction + one two-input affine pass:
+        dbeta = sum_n dy,  dgamma = sum_n dy xhat,
+        dx = rstd (gamma dy - mean_g(gamma dy) - xhat mean_g(gamma dy xhat)).
+    x [B, N, C] fp32 contiguous, gamma / beta [B, C]."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float):
+        B, N, C = x.shape
+        gs = C // groups
+        x = x.contiguous()
+        stats = ops.group_stats(x.view(B * N, C), N, N, gs)  # [B, G, 2] float64
+        n = float(N * gs)
+        mean = stats[..., 0] / n
+        var = (stats[..., 1] / n - mean * mean).clamp_min(0.0)
+        rstd_c = (var + eps).rsqrt().float().repeat_interleave(gs, dim=1)  # [B, C]
+        mean_c = mean.float().repeat_interleave(gs, dim=1)
+        p = (gamma * rstd_c).contiguous()
+        y = ops.train_affine(x, None, p, None, (beta - p * mean_c).contiguous())
+        ctx.save_for_backward(x, gamma, mean_c, rstd_c)
+        ctx.gs, ctx.n = gs, n
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, gamma, mean_c, rstd_c = ctx.saved_tensors
+        B, N, C = x.shape
+        gs, n = ctx.gs, ctx.n
+        dy = dy.contiguous()
+        T = ops.train_colsum2(dy, x)
+        t1, t2 = T[..., 0], T[..., 1]
+        dgamma = rstd_c * (t2 - mean_c * t1)
+        grp = lambda v: v.view(B, C // gs, gs).sum(-1, keepdim=True).expand(B, C // gs, gs).reshape(B, C)
+        a_c, b_c = grp(gamma * t1), grp(gamma * dgamma)
+        r2 = rstd_c * rstd_c
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.train_affine(dy, x, (rstd_c * gamma).contiguous(), (-r2 * b_c / n).contiguous(),
+                                  ((r2 * mean_c * b_c - rstd_c * a_c) / n).contiguous())
+        return dx, dgamma, t1, None, None
+
+
+class GaussAct(torch.autograd.Function):
+    """models/activation.py:17-24 in one pass forward and one backward (alpha stays on the device: graph-safe)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, alpha: Tensor, normalized: bool):
+        x = x.contiguous()
+        a = alpha.detach().reshape(()).float()
+        ctx.save_for_backward(x, a)
+        ctx.normalized, ctx.alpha_shape = normalized, alpha.shape
+        return ops.train_gauss_act_fwd(x, a, normalized)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, a = ctx.saved_tensors
+        dx, dalpha = ops.train_gauss_act_bwd(x, dy.contiguous(), a, ctx.normalized)
+        return dx, dalpha.reshape(ctx.alpha_shape), None
+
+
+def _use_kernels(x: Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 1024 and _fused()
+
+
 def adagn(mod, x: Tensor, t: Tensor) -> Tensor:
     """models/normalization.py:36-44: GroupNorm over (points x channels-in-group), then the t-conditioned affine."""
-    normed = F.group_norm(x.transpose(1, 2), mod.gn.num_groups, eps=mod.gn.eps).transpose(1, 2)
     scale = F.linear(t, mod.scale.weight, mod.scale.bias)
     bias = F.linear(t, mod.bias.weight, mod.bias.bias)
+    if _use_kernels(x) and x.shape[-1] % mod.gn.num_groups == 0:
+        B, _, C = x.shape
+        return GroupAffineNorm.apply(x, scale.reshape(B, C), bias.reshape(B, C), mod.gn.num_groups, mod.gn.eps)
+    normed = F.group_norm(x.transpose(1, 2), mod.gn.num_groups, eps=mod.gn.eps).transpose(1, 2)
     return scale * normed + bias
 
 
 def gaussian_activation(act, x: Tensor) -> Tensor:
     """models/activation.py:17-24."""
+    if x.is_cuda and x.dtype == torch.float32 and _fused():
+        return GaussAct.apply(x, act.alpha, bool(act.normalized))
     y = (-(x**2) / (2 * act.alpha**2)).exp()
     return (y - 0.7) / 0.28 if act.normalized else y
 
@@ -248,6 +324,11 @@ def extract_image_features(net, geometry_diffusion: Tensor, features: Sequence[T
 
 def _group_norm_bnc(mod, x: Tensor) -> Tensor:
     """models/ray.py:20-30."""
+    if _use_kernels(x) and x.shape[-1] % mod.num_groups == 0:
+        B, _, C = x.shape
+        w = x.new_ones(B, C) if mod.weight is None else mod.weight.expand(B, C)
+        b = x.new_zeros(B, C) if mod.bias is None else mod.bias.expand(B, C)
+        return GroupAffineNorm.apply(x, w, b, mod.num_groups, mod.eps)
     return F.group_norm(x.transpose(1, 2), mod.num_groups, mod.weight, mod.bias, mod.eps).transpose(1, 2)
 
 

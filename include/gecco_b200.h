@@ -476,6 +476,28 @@ int gecco_upsample_step(gecco_engine* e, const gecco_upsample_step_args* args, v
 int gecco_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, int64_t step, double lr,
                         double beta1, double beta2, double eps, double grad_scale, double ema_decay, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Element-wise kernels of the training step's autograd functions (gecco_b200/training.py), one HBM-bound pass each:
+ *   GaussianActivation (models/activation.py:17-24), forward and backward, with alpha as a DEVICE scalar (no host
+ *   read-back: the step is captured as a CUDA graph); the backward writes gecco_train_gauss_act_bwd_parts(n) partial
+ *   sums of dalpha (one per block; the caller adds them up in a fixed order -- deterministic, no atomics);
+ *   the two kernels of AdaGN / GroupNorm (models/normalization.py:36-44, models/ray.py:20-30) around gecco_group_stats:
+ *     affine : out[b,n,c] = p[b,c] * u[b,n,c] (+ q[b,c] * w[b,n,c]) + r[b,c]   (w, q both NULL or both given)
+ *              forward y = gamma * xhat + beta with (u = x) and the input gradient with (u = dy, w = x);
+ *     colsum2: out[b,part,c,0] = partial sum_n dy[b,n,c], out[b,part,c,1] = partial sum_n dy[b,n,c] * x[b,n,c] for the
+ *              gecco_train_colsum2_parts(rows_per_cloud, c) row partitions of a cloud (the caller sums over `part`).
+ * All tensors contiguous fp32 [clouds, rows_per_cloud, c], c a multiple of 4 (<= 1024), 16-byte aligned.
+ * ------------------------------------------------------------------------ */
+int gecco_train_gauss_act_fwd(const float* x, const float* alpha, float* y, int64_t n, int32_t normalized, void* stream);
+int64_t gecco_train_gauss_act_bwd_parts(int64_t n);
+int gecco_train_gauss_act_bwd(const float* x, const float* dy, const float* alpha, float* dx, float* dalpha, int64_t n,
+                              int32_t normalized, void* stream);
+int gecco_train_affine(const float* u, const float* w, const float* p, const float* q, const float* r, float* out,
+                       int32_t clouds, int32_t rows_per_cloud, int32_t c, void* stream);
+int32_t gecco_train_colsum2_parts(int32_t rows_per_cloud, int32_t c);
+int gecco_train_colsum2(const float* dy, const float* x, float* out, int32_t clouds, int32_t rows_per_cloud, int32_t c,
+                        void* stream);
+
 /* Per-kernel-class device timing of the engine (tracing aid; the reference has none).  Between
  * start and stop every engine launch on this thread is bracketed by CUDA events on its stream; stop synchronises
  * the device and returns, per class, the launch count, summed device time and the algorithmic FLOPs / bytes. */

@@ -227,3 +227,47 @@ def test_graphed_step_matches_eager(cuda):
     assert abs(a0 - b0) <= 1e-5 * abs(a0) and abs(a1 - b1) <= 1e-3 * abs(a1)
     assert rms(ga - gb) <= 1e-4 * rms(ga)
     assert rms(pa - pb) <= 1e-4 * rms(pa)
+
+
+@pytest.mark.parametrize("B,N,C,groups", [(3, 200, 384, 32), (2, 77, 672, 16), (1, 64, 384, 32)])
+def test_group_affine_norm_kernels_match_torch(cuda, B, N, C, groups):
+    """GroupAffineNorm (gecco_group_stats + gecco_train_affine / gecco_train_colsum2) against the torch expression of
+    models/normalization.py:36-44 in float64: output and the gradients of x, gamma, beta."""
+    from gecco_b200 import training as T
+
+    g = torch.Generator("cpu").manual_seed(B * 1000 + N)
+    x = (torch.randn(B, N, C, generator=g) * 1.7 + 0.4).to(cuda).requires_grad_(True)
+    gamma = (torch.randn(B, C, generator=g) * 0.3 + 1.0).to(cuda).requires_grad_(True)
+    beta = (torch.randn(B, C, generator=g) * 0.2).to(cuda).requires_grad_(True)
+    dy = torch.randn(B, N, C, generator=g).to(cuda)
+    y = T.GroupAffineNorm.apply(x, gamma, beta, groups, 1e-5)
+    gx, gg, gb = torch.autograd.grad(y, (x, gamma, beta), dy)
+    xd, gd, bd = (t.detach().double().requires_grad_(True) for t in (x, gamma, beta))
+    ref = gd[:, None] * torch.nn.functional.group_norm(xd.transpose(1, 2), groups, eps=1e-5).transpose(1, 2) + bd[:, None]
+    rx, rg, rb = torch.autograd.grad(ref, (xd, gd, bd), dy.double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    errs = dict(y=rel(y, ref), dx=rel(gx, rx), dgamma=rel(gg, rg), dbeta=rel(gb, rb))
+    print("GroupAffineNorm", (B, N, C, groups), errs)
+    assert max(errs.values()) < 2e-5, errs
+
+
+@pytest.mark.parametrize("normalized", [True, False])
+def test_gauss_act_kernels_match_torch(cuda, normalized):
+    """GaussAct (models/activation.py:17-24) forward / backward kernels against torch in float64, odd element count."""
+    from gecco_b200 import training as T
+
+    g = torch.Generator("cpu").manual_seed(5)
+    x = (torch.randn(3, 37, 771, generator=g) * 1.5).to(cuda).requires_grad_(True)
+    alpha = torch.tensor(1.3, device=cuda, requires_grad=True)
+    dy = torch.randn(3, 37, 771, generator=g).to(cuda)
+    y = T.GaussAct.apply(x, alpha, normalized)
+    gx, ga = torch.autograd.grad(y, (x, alpha), dy)
+    xd, ad = x.detach().double().requires_grad_(True), alpha.detach().double().requires_grad_(True)
+    ref = (-(xd**2) / (2 * ad**2)).exp()
+    if normalized:
+        ref = (ref - 0.7) / 0.28
+    rx, ra = torch.autograd.grad(ref, (xd, ad), dy.double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    errs = dict(y=rel(y, ref), dx=rel(gx, rx), dalpha=abs(ga.item() - ra.item()) / abs(ra.item()))
+    print("GaussAct", normalized, errs)
+    assert errs["y"] < 5e-6 and errs["dx"] < 5e-6 and errs["dalpha"] < 1e-4, errs
