@@ -60,9 +60,12 @@ struct PParams {
   const float* n_t; int n_t_stride;
   const float *n_scale_w, *n_scale_b, *n_bias_w, *n_bias_b;
   int K;
+  int rev;  // row blocks are walked from the end (the previous kernel's last writes are read first, while still in L2)
 };
 
 __device__ __forceinline__ int num_kb_of(const PParams& p) { return p.num_kb; }
+// physical row block of the pb-th one this pair processes
+#define RB(pb) (p.rev ? p.num_pair_blocks - 1 - (pb) : (pb))
 
 // cycles spent in a barrier wait, accumulated into `acc` when the debug buffer is set
 #define TIMED_WAIT(acc, bar, parity)        \
@@ -168,7 +171,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     long long w_aempty = 0, w_bempty = 0;
     const long long t_start = clock64();
     for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs, ++it) {
-      const int m0 = pb * 2 * BM + (int)rank * BM;
+      const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
       const int cloud_w = p.w_rows_per_cloud ? (m0 / p.e.rows_per_cloud) * p.w_rows_per_cloud : 0;
       for (int nb = 0; nb < p.num_n_blocks; ++nb) {
         const int wrow = cloud_w + nb * BN + (int)rank * BNH;
@@ -266,7 +269,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // (mean = s1 / n and E[x^2] - mean^2 need the precision, rstd does not) and the statistics loads are issued first.
     const double inv_count = 1.0 / count;
     auto make_norm = [&](int pb, uint32_t buf) {
-      const int m0 = pb * 2 * BM + (int)rank * BM;
+      const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
       const int cloud = m0 / p.e.rows_per_cloud;
       const double* cst = p.n_stats + (long long)cloud * (K / p.n_stat_gs) * 2;
       float* na = sNorm + buf * 2 * MAX_KB * BK;
@@ -358,7 +361,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (p.e.has_res && !(p.e.skip & 2)) {
       uint32_t cnt[EPI_GROUPS] = {0, 0};
       for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs) {
-        const int m0 = pb * 2 * BM + (int)rank * BM;
+        const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
         for (int nb = 0; nb < p.num_n_blocks; ++nb) epi_load_residual_panel(p.e, es, &tma_res, m0, nb * BN, cnt);
       }
     }
@@ -372,9 +375,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     long long w_accfull = 0, w_pref = 0;
     const long long t_start = clock64();
     EpiBias bias_r;
-    if (pair < p.num_pair_blocks) epi_bias_load(p.e, et, pair * 2 * BM + (int)rank * BM, 0, bias_r);
+    if (pair < p.num_pair_blocks) epi_bias_load(p.e, et, RB(pair) * 2 * BM + (int)rank * BM, 0, bias_r);
     for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs) {
-      const int m0 = pb * 2 * BM + (int)rank * BM;
+      const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
       for (int nb = 0; nb < p.num_n_blocks; ++nb, ++tile) {
         const uint32_t slot = tile & 1u;
         long long tp0 = 0;
@@ -382,7 +385,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         epi_bias_stage(p.e, et, bias_r);
         // the next panel's bias is loaded under this panel
         if (nb + 1 < p.num_n_blocks) epi_bias_load(p.e, et, m0, (nb + 1) * BN, bias_r);
-        else if (pb + num_pairs < p.num_pair_blocks) epi_bias_load(p.e, et, (pb + num_pairs) * 2 * BM + (int)rank * BM, 0, bias_r);
+        else if (pb + num_pairs < p.num_pair_blocks) epi_bias_load(p.e, et, RB(pb + num_pairs) * 2 * BM + (int)rank * BM, 0, bias_r);
         if (GECCO_DBG_ON(p.dbg)) w_pref += clock64() - tp0;
         TIMED_WAIT(w_accfull, &acc_full[slot], (tile >> 1) & 1u);
         tc_fence_after_sync();
@@ -432,6 +435,15 @@ bool fast_epilogue_enabled() {
   return g_fast_epilogue != 0;
 }
 void set_fast_epilogue_option(int value) { g_fast_epilogue = value != 0 ? 1 : 0; }
+
+// GECCO_REV (bit mask): 1 residual projections (unpool out-proj), 4 normalising projections (k|v|q) walk the row blocks backwards
+static int pair_rev(const gecco_gemm_args& a) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GECCO_REV"); v = e ? atoi(e) : 2; }
+  if (a.res != nullptr) return (v & 1) ? 1 : 0;
+  if (a.anorm.stats != nullptr) return (v & 4) ? 1 : 0;
+  return 0;
+}
 
 bool gemm_pair_shape_ok(int m, int rows_per_cloud, int n_out, int k) {
   if (k > MAX_KB * BK || k % 8 != 0 || m % (2 * BM) != 0 || m < 2 * BM * 8 || sm_count() < 2) return false;
@@ -490,6 +502,7 @@ int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t stream, int* handled
   p.n_t = a.anorm.t; p.n_t_stride = a.anorm.t_stride;
   p.n_scale_w = a.anorm.scale_w; p.n_scale_b = a.anorm.scale_b; p.n_bias_w = a.anorm.bias_w; p.n_bias_b = a.anorm.bias_b;
   p.K = a.k;
+  p.rev = pair_rev(a);
   // bf16-only whole-tile projections take the fast epilogue
   const bool fast = fast_epilogue_enabled() && a.res == nullptr && a.stats == nullptr && a.out_f32 == nullptr && a.geom == nullptr &&
                     a.bias != nullptr && a.out_bf16 != nullptr && a.n_out % BN == 0 &&
@@ -500,6 +513,10 @@ int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t stream, int* handled
   p.kbps = 1;
   for (int cand = p.num_kb; cand > 1; --cand)  // deepest weight stage that still leaves a 3-deep ring
     if (p.num_kb % cand == 0 && avail / (cand * B_STAGE_BYTES) >= 3) { p.kbps = cand; break; }
+  if (const char* v = getenv("GECCO_PAIR_KBPS")) {  // development aid: k-blocks per weight stage
+    const int want = atoi(v);
+    if (want >= 1 && p.num_kb % want == 0 && avail / (want * B_STAGE_BYTES) >= 2) p.kbps = want;
+  }
   p.bstages = avail / (p.kbps * B_STAGE_BYTES);
   if (p.bstages > MAX_BSTAGES) p.bstages = MAX_BSTAGES;
   GECCO_REQUIRE(p.bstages >= 2, "gemm_pair: shared memory budget");

@@ -64,9 +64,12 @@ struct MParams {
   const float* n_t; int n_t_stride;
   const float *n_scale_w, *n_scale_b, *n_bias_w, *n_bias_b;
   long long* dbg;
+  int rev;    // GECCO_REV & 2: row blocks are walked from the end
+  int respf;  // GECCO_MLP_RESPF (development): 0 residual tile -> L2 at the start of the second product, 1 per output tile, 2 never
 };
 
 // development aid: cycles spent in a barrier wait, accumulated when the debug buffer is set (gecco_set_debug_buffer)
+#define RB(pb) (p.rev ? p.num_pair_blocks - 1 - (pb) : (pb))
 #define TW(acc, bar, parity)              \
   do {                                    \
     if (p.dbg != nullptr) {               \
@@ -280,7 +283,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       long long w_b1 = 0, w_a = 0, w_hr = 0, w_hs = 0, w_b2 = 0;
       const long long t_start = clock64();
       for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs, ++it) {
-        const int m0 = pb * 2 * BM + (int)rank * BM;
+        const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
         // first product: A k-blocks once per row block, W1 half tiles per (tile, k-block)
         for (int nb = 0; nb < NU; ++nb) {
           const int wrow = nb * BN + (int)rank * BNH;
@@ -297,12 +300,17 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
         }
         // the residual tile of this row block and the A tile of the next one -> L2
-        for (int c = 0; c < C / EPI_CHUNK; ++c) tma_prefetch_l2_2d(&tma_res, c * EPI_CHUNK, m0);
-        if (pb + num_pairs < p.num_pair_blocks)
-          for (int kb = 0; kb < KB1; ++kb) tma_prefetch_l2_2d(&tma_a, kb * BK, (pb + num_pairs) * 2 * BM + (int)rank * BM);
+        if ((p.respf & 3) == 0)
+          for (int c = 0; c < C / EPI_CHUNK; ++c) tma_prefetch_l2_2d(&tma_res, c * EPI_CHUNK, m0);
+        if (((p.respf >> 2) & 3) == 0 && pb + num_pairs < p.num_pair_blocks)
+          for (int kb = 0; kb < KB1; ++kb) tma_prefetch_l2_2d(&tma_a, kb * BK, RB(pb + num_pairs) * 2 * BM + (int)rank * BM);
         // second product: hidden k-blocks from the scratch through the slots of the A tile, W2 half tiles
         for (int nb = 0; nb < ND; ++nb) {
           const int wrow = nb * BN + (int)rank * BNH;
+          if ((p.respf & 3) == 1)
+            for (int c = 0; c < BN / EPI_CHUNK; ++c) tma_prefetch_l2_2d(&tma_res, nb * BN + c * EPI_CHUNK, m0);
+          if (((p.respf >> 2) & 3) == 1 && nb == ND - 1 && pb + num_pairs < p.num_pair_blocks)
+            for (int kb = 0; kb < KB1; ++kb) tma_prefetch_l2_2d(&tma_a, kb * BK, RB(pb + num_pairs) * 2 * BM + (int)rank * BM);
           for (int kb = 0; kb < KB2; ++kb) {
             const int slot = kb % KB1;
             const uint32_t fill = it * 5u + 1u + (uint32_t)(nb * 2 + kb / KB1);
@@ -395,7 +403,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int gs = C / p.n_groups;
       const double inv_count = 1.0 / ((double)p.d.valid_rows * gs);
       auto make_norm = [&](int pb, uint32_t buf) {
-        const int m0 = pb * 2 * BM + (int)rank * BM;
+        const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
         const int cloud = m0 / p.d.rows_per_cloud;
         const double* cst = p.n_stats + (long long)cloud * (C / p.n_stat_gs) * 2;
         float* na = sNorm + buf * 2 * C;
@@ -476,9 +484,9 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     ResRegs R;
     long long e_accu = 0, e_fast = 0, e_store = 0, e_accd = 0, e_panel = 0;
     const long long e_start = clock64();
-    if (pair < p.num_pair_blocks) epi_bias_load(p.u, et, pair * 2 * BM + (int)rank * BM, 0, bias_r);
+    if (pair < p.num_pair_blocks) epi_bias_load(p.u, et, RB(pair) * 2 * BM + (int)rank * BM, 0, bias_r);
     for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs, ++it) {
-      const int m0 = pb * 2 * BM + (int)rank * BM;
+      const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
       const bool row_valid = (m0 % p.u.rows_per_cloud) + q * 32 + (int)et.lane < p.u.valid_rows;
       for (int nb = 0; nb < NU; ++nb, ++tile) {
         const uint32_t slot = tile & 1u;
@@ -509,7 +517,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         const uint32_t slot = tile & 1u;
         epi_bias_stage(p.d, et, bias_r);
         if (nb + 1 < ND) epi_bias_load(p.d, et, m0, (nb + 1) * BN, bias_r);
-        else if (pb + num_pairs < p.num_pair_blocks) epi_bias_load(p.u, et, (pb + num_pairs) * 2 * BM + (int)rank * BM, 0, bias_r);
+        else if (pb + num_pairs < p.num_pair_blocks) epi_bias_load(p.u, et, RB(pb + num_pairs) * 2 * BM + (int)rank * BM, 0, bias_r);
         TW(e_accd, &acc_full[slot], (tile >> 1) & 1u);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * ACC_COLS;
@@ -590,6 +598,12 @@ int launch_mlp_pair(const gecco_mlp_args& a, cudaStream_t stream) {
   p.n_t = a.anorm.t; p.n_t_stride = a.anorm.t_stride;
   p.n_scale_w = a.anorm.scale_w; p.n_scale_b = a.anorm.scale_b; p.n_bias_w = a.anorm.bias_w; p.n_bias_b = a.anorm.bias_b;
   p.dbg = g_gemm_debug;
+  static int respf = -1;
+  if (respf < 0) { const char* v = getenv("GECCO_MLP_RESPF"); respf = v ? atoi(v) : 1; }
+  p.respf = respf;
+  static int rev = -1;
+  if (rev < 0) { const char* v = getenv("GECCO_REV"); rev = v ? atoi(v) : 2; }
+  p.rev = (rev & 2) ? 1 : 0;
 
   static bool attr_set = false;
   if (!attr_set) {
