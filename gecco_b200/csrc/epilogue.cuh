@@ -44,6 +44,7 @@ struct EpiParams {
   const float* wx;  // [n_out, 3]
   int skip;         // development aid (gecco_set_option("epi_skip")): 1 no output stores, 2 no residual, 4 no proxy fence, 8 no statistics atomics
   long long* dbg;   // development aid: [grid][32] cycle counters, slots 16..21 (nullptr in production)
+  int hints;        // L2 residency hints (ptx.cuh l2_policy kinds): bits 2-3 residual loads, 4-5 fp32 stores, 6-7 bf16 stores
 };
 
 struct EpiSmem {
@@ -81,21 +82,22 @@ __device__ __forceinline__ void epi_bar_init(const EpiSmem& es) {
 
 // Loader side (one thread): the residual chunk at column col0 for group g; cnt = chunks loaded for that group so far.
 __device__ __forceinline__ void epi_load_residual_chunk(const EpiSmem& sm, const CUtensorMap* tma_res, int m0, int col0,
-                                                        int g, uint32_t& cnt) {
+                                                        int g, uint32_t& cnt, uint64_t pol) {
   const uint32_t b = cnt & 1u, phase = (cnt >> 1) & 1u;
   mbar_wait(&sm.res_empty[g * 2 + b], phase ^ 1u);
   mbar_arrive_expect_tx(&sm.res_full[g * 2 + b], EPI_RES_BYTES);
-  tma_load_2d((b ? sm.x1 : sm.x0) + g * EPI_RES_BYTES, tma_res, &sm.res_full[g * 2 + b], col0, m0);
+  tma_load_2d_h((b ? sm.x1 : sm.x0) + g * EPI_RES_BYTES, tma_res, &sm.res_full[g * 2 + b], col0, m0, pol);
   ++cnt;
 }
 // The residual chunks of one panel in the order the epilogue consumes them (chunk c belongs to group c & 1).
 __device__ __forceinline__ void epi_load_residual_panel(const EpiParams& p, const EpiSmem& sm, const CUtensorMap* tma_res,
                                                         int m0, int n0, uint32_t (&cnt)[EPI_GROUPS]) {
+  const uint64_t pol = l2_policy((p.hints >> 2) & 3);
 #pragma unroll 1
   for (int c = 0; c < EPI_PANEL / EPI_CHUNK; ++c) {
     const int col0 = n0 + c * EPI_CHUNK;
     if (col0 >= p.n_out) break;
-    epi_load_residual_chunk(sm, tma_res, m0, col0, c & 1, cnt[c & 1]);
+    epi_load_residual_chunk(sm, tma_res, m0, col0, c & 1, cnt[c & 1], pol);
   }
 }
 
@@ -301,8 +303,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, const EpiSmem& sm,
   __syncwarp();
   if (GECCO_DBG_ON(p.dbg)) tf2__ = clock64();
   if (elect_one() && !(p.skip & 1)) {  // lane 0 (the bulk groups are per thread: the same lane waits for them)
-    if (p.o32 != nullptr) tma_store_2d_addr(tma_o32, xs, col0, m0 + t.q * 32);
-    if (p.o16 != nullptr) tma_store_2d_addr(tma_o16, t.s16, col0, m0 + t.q * 32);
+    if (p.o32 != nullptr) tma_store_2d_addr_h(tma_o32, xs, col0, m0 + t.q * 32, l2_policy((p.hints >> 4) & 3));
+    if (p.o16 != nullptr) tma_store_2d_addr_h(tma_o16, t.s16, col0, m0 + t.q * 32, l2_policy((p.hints >> 6) & 3));
     tma_store_commit();
   }
   if (GECCO_DBG_ON(p.dbg) && t.lane == 0 && t.q == 0 && t.grp == 0) {
@@ -452,7 +454,7 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, const EpiThrea
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
-        tma_store_2d_addr(tma_o16, wst, n0 + (2 * k + t.grp) * EPI_CHUNK, m0 + t.q * 32);
+        tma_store_2d_addr_h(tma_o16, wst, n0 + (2 * k + t.grp) * EPI_CHUNK, m0 + t.q * 32, l2_policy((p.hints >> 6) & 3));
         tma_store_commit();
       }
     }

@@ -60,6 +60,7 @@ struct PParams {
   const float* n_t; int n_t_stride;
   const float *n_scale_w, *n_scale_b, *n_bias_w, *n_bias_b;
   int K;
+  int a_hint;  // L2 residency hint of the A-operand loads (ptx.cuh l2_policy kinds)
   int rev;  // row blocks are walked from the end (the previous kernel's last writes are read first, while still in L2)
 };
 
@@ -170,6 +171,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t it = 0;
     long long w_aempty = 0, w_bempty = 0;
     const long long t_start = clock64();
+    const uint64_t a_pol = l2_policy(p.a_hint);
     for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs, ++it) {
       const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
       const int cloud_w = p.w_rows_per_cloud ? (m0 / p.e.rows_per_cloud) * p.w_rows_per_cloud : 0;
@@ -186,12 +188,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 // then complete the leader's a_full[kb]
                 TIMED_WAIT(w_aempty, &a_empty[kb], (it & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&a_landed[kb], A_KB_BYTES);
-                tma_load_2d(sA + kb * A_KB_BYTES, &tma_a, &a_landed[kb], kb * BK, m0);
+                tma_load_2d_h(sA + kb * A_KB_BYTES, &tma_a, &a_landed[kb], kb * BK, m0, a_pol);
               } else {
                 // this CTA's 128 rows of A, k-block kb: resident for all column blocks of the row block
                 TIMED_WAIT(w_aempty, &a_empty[kb], (it & 1u) ^ 1u);
                 if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * A_KB_BYTES);
-                tma_load_2d_pair(sA + kb * A_KB_BYTES, &tma_a, &a_full[kb], kb * BK, m0);
+                tma_load_2d_pair_h(sA + kb * A_KB_BYTES, &tma_a, &a_full[kb], kb * BK, m0, a_pol);
               }
             }
             tma_load_2d_pair(sB + stage * stage_bytes + kk * B_STAGE_BYTES, &tma_w, &b_full[stage], kb * BK, wrow);
@@ -498,6 +500,16 @@ int launch_gemm_pair(const gecco_gemm_args& a, cudaStream_t stream, int* handled
   p.dbg = g_gemm_debug;
   p.e.dbg = g_gemm_debug;
   p.e.skip = epi_skip_option();
+  {
+    // L2 residency hints per launch class (bits 0-1 A loads, 2-3 residual loads, 4-5 fp32 stores, 6-7 bf16 stores):
+    // GECCO_HINT_OUT residual projections (unpool out-proj), GECCO_HINT_KVQ normalising projections (k|v|q)
+    static int h_out = -1, h_kvq = -1;
+    if (h_out < 0) { const char* e = getenv("GECCO_HINT_OUT"); h_out = e ? atoi(e) : 160; }  // both outputs evict_last: the MLP reads them next
+    if (h_kvq < 0) { const char* e = getenv("GECCO_HINT_KVQ"); h_kvq = e ? atoi(e) : 0; }
+    const int h = a.res != nullptr ? h_out : (a.anorm.stats != nullptr ? h_kvq : 0);
+    p.e.hints = h;
+    p.a_hint = h & 3;
+  }
   p.n_stats = a.anorm.stats; p.n_stat_gs = a.anorm.stat_gs; p.n_groups = a.anorm.groups; p.n_eps = a.anorm.eps;
   p.n_t = a.anorm.t; p.n_t_stride = a.anorm.t_stride;
   p.n_scale_w = a.anorm.scale_w; p.n_scale_b = a.anorm.scale_b; p.n_bias_w = a.anorm.bias_w; p.n_bias_b = a.anorm.bias_b;

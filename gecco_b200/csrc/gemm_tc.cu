@@ -354,6 +354,7 @@ int launch_gemm(const gecco_gemm_args& a, cudaStream_t stream) {
   p.e.geom = a.geom; p.e.sigma = a.sigma; p.e.sigma_stride = a.sigma_stride; p.e.sigma_data = a.sigma_data; p.e.wx = a.wx;
   p.e.dbg = nullptr;
   p.e.skip = 0;
+  p.e.hints = 0;
   p.num_m_blocks = ceil_div(a.m, BM);
   p.num_n_blocks = ceil_div(a.n_out, BN);
   const int epi_bytes = epi_smem_bytes(p.e.has_res, a.out_f32 != nullptr, a.out_bf16 != nullptr);

@@ -294,10 +294,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int m0 = pb * 2 * BM + (int)rank * BM;
           // every group starts a row block on its dedicated buffer: the first chunk of each group is loaded ahead of the
           // epilogue; the second buffers alias the hidden chunk, which the second GEMM reads until Y is complete
-          epi_load_residual_chunk(es, &tma_res, m0, 0, 0, cnt[0]);
-          epi_load_residual_chunk(es, &tma_res, m0, EPI_CHUNK, 1, cnt[1]);
+          epi_load_residual_chunk(es, &tma_res, m0, 0, 0, cnt[0], l2_policy(0));
+          epi_load_residual_chunk(es, &tma_res, m0, EPI_CHUNK, 1, cnt[1], l2_policy(0));
           mbar_wait(y_full, it & 1u);
-          for (int c = 2; c < C / EPI_CHUNK; ++c) epi_load_residual_chunk(es, &tma_res, m0, c * EPI_CHUNK, c & 1, cnt[c & 1]);
+          for (int c = 2; c < C / EPI_CHUNK; ++c) epi_load_residual_chunk(es, &tma_res, m0, c * EPI_CHUNK, c & 1, cnt[c & 1], l2_policy(0));
         }
       }
     }
@@ -440,6 +440,7 @@ int launch_mlp_fused(const gecco_mlp_args& a, cudaStream_t stream) {
   p.dbg = g_gemm_debug;
   p.e.dbg = g_gemm_debug;
   p.e.skip = epi_skip_option();
+  p.e.hints = 0;
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -64,6 +64,7 @@ struct MParams {
   const float* n_t; int n_t_stride;
   const float *n_scale_w, *n_scale_b, *n_bias_w, *n_bias_b;
   long long* dbg;
+  int hints;  // GECCO_HINT_MLP: L2 residency hints, bits 0-1 A loads, 2-3 residual loads, 4-5 fp32 stores, 6-7 bf16 stores
   int rev;    // GECCO_REV & 2: row blocks are walked from the end
   int respf;  // GECCO_MLP_RESPF (development): 0 residual tile -> L2 at the start of the second product, 1 per output tile, 2 never
 };
@@ -84,9 +85,9 @@ struct MParams {
 // Waits until all bulk stores of this thread have COMPLETED (their global writes are visible), not only read their source.
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ float4 ldg128(const float* p) {
+__device__ __forceinline__ float4 ldg128(const float* p, uint64_t pol) {
   float4 v;
-  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
 
@@ -94,8 +95,9 @@ __device__ __forceinline__ float4 ldg128(const float* p) {
 struct ResRegs { float4 r[8]; };
 __device__ __forceinline__ void res_load(const MParams& p, int row0, int col0, int lane, ResRegs& R) {
   const float* base = p.res + (long long)(row0 + (lane >> 3)) * p.ldr + col0 + (lane & 7) * 4;
+  const uint64_t pol = l2_policy((p.hints >> 2) & 3);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) R.r[i] = ldg128(base + (long long)(4 * i) * p.ldr);
+  for (int i = 0; i < 8; ++i) R.r[i] = ldg128(base + (long long)(4 * i) * p.ldr, pol);
 }
 __device__ __forceinline__ void res_stage(uint32_t xs, int lane, const ResRegs& R) {
 #pragma unroll
@@ -190,8 +192,8 @@ __device__ __forceinline__ void epi_panel_ldg(const MParams& p, const EpiThread&
     fence_proxy_async_smem();
     __syncwarp();
     if (elect_one()) {
-      tma_store_2d_addr(tma_o32, xs, col0, row0);
-      tma_store_2d_addr(tma_o16, t.s16, col0, row0);
+      tma_store_2d_addr_h(tma_o32, xs, col0, row0, l2_policy((p.hints >> 4) & 3));
+      tma_store_2d_addr_h(tma_o16, t.s16, col0, row0, l2_policy((p.hints >> 6) & 3));
       tma_store_commit();
     }
   };
@@ -293,7 +295,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (nb == 0) {
               TW(w_a, &a_empty[kb], ((it * 5u) & 1u) ^ 1u);  // fill 5 it of the slot
               mbar_arrive_expect_tx(&a_landed[kb], A_KB_BYTES);
-              tma_load_2d(sA + kb * A_KB_BYTES, &tma_a, &a_landed[kb], kb * BK, m0);
+              tma_load_2d_h(sA + kb * A_KB_BYTES, &tma_a, &a_landed[kb], kb * BK, m0, l2_policy(p.hints & 3));
             }
             tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tma_w1, &b_full[stage], kb * BK, wrow);
             if (++stage == BST) { stage = 0; bphase ^= 1u; }
@@ -604,6 +606,9 @@ int launch_mlp_pair(const gecco_mlp_args& a, cudaStream_t stream) {
   static int rev = -1;
   if (rev < 0) { const char* v = getenv("GECCO_REV"); rev = v ? atoi(v) : 2; }
   p.rev = (rev & 2) ? 1 : 0;
+  static int hints = -1;
+  if (hints < 0) { const char* v = getenv("GECCO_HINT_MLP"); hints = v ? atoi(v) : 5; }  // A and residual are read once: evict_first
+  p.hints = hints;
 
   static bool attr_set = false;
   if (!attr_set) {
