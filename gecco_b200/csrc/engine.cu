@@ -320,11 +320,20 @@ bool fused_mlp_enabled() {
     if (rc__ != 0) return rc__;        \
   } while (0)
 
+// Key / value projections (and V^T) of the cached inducer states, per layer.  They depend on the cache only, so the
+// upsampling step computes them ONCE in its caching evaluation (mode 1) and its 2 * num_substeps cached evaluations read
+// them (mode 2) instead of re-packing the cache and re-projecting it in every layer of every evaluation.
+struct KvCache {
+  __nv_bfloat16* khv;  // [layers][clouds * I, 2 C]
+  __nv_bfloat16* vt;   // [layers][clouds * C, I]
+  int mode;            // 1 write, 2 read
+};
+
 // One evaluation.  `xin` is the raw (un-scaled) [clouds, points, 3] input; the head arguments select what is
 // produced (see gecco_head_args modes).
 int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float* sigma, int sigma_stride, float sigma_imm,
              const float* t_embed, int t_stride, int clouds, int points, const gecco_context& ctx, const float* cache_in, float* cache_out,
-             gecco_head_args head, cudaStream_t s) {
+             gecco_head_args head, cudaStream_t s, const KvCache* kvc = nullptr) {
   const gecco_model_desc& d = e->d;
   const int C = d.feature_dim, I = d.num_inducers, H = d.num_heads, hid = d.mlp_hidden, hd = C / H;
   const int sg = d.adagn_groups, Np = w.Np, rows = w.rows, irows = w.irows;
@@ -448,7 +457,11 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
     ch.act_alpha = L.bmlp_alpha;
     for (int i = 0; i < 4; ++i) { ch.norm[0][i] = lw[GECCO_LW_N1 + i]; ch.norm[1][i] = lw[GECCO_LW_N2 + i]; }
     ch.t = w.c_noise; ch.t_stride = 1; ch.eps = 1e-5f;
-    ch.hn = w.hn; ch.hh = w.hh; ch.h3 = w.h3; ch.khv = w.khv; ch.vt = w.vt;
+    // key / value projections of this layer's inducer states: the workspace buffers, or the per-layer slots of the
+    // upsampling step's cache
+    __nv_bfloat16* khv_l = kvc ? kvc->khv + (size_t)l * irows * 2 * C : w.khv;
+    __nv_bfloat16* vt_l = kvc ? kvc->vt + (size_t)l * irows * C : w.vt;
+    ch.hn = w.hn; ch.hh = w.hh; ch.h3 = w.h3; ch.khv = khv_l; ch.vt = vt_l;
     const bool chain = chain_enabled() && inducer_chain_supported(ch);
     bool kv_done = false;
     if (pooling && chain) {
@@ -488,6 +501,8 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       a.out_bf16 = w.h3; a.ldo16 = C;
       if (cache_out != nullptr) { a.out_f32 = cache_out + (size_t)l * irows * C; a.ldo32 = C; }
       TRYP(K_INDUCER_CHAIN, 2 * Mi * Cd, Mi * Cd * 6, launch_adagn(a, s));
+    } else if (kvc != nullptr && kvc->mode == 2) {
+      kv_done = true;  // projected once by the caching evaluation of this noise level
     } else {
       const long long n = (long long)irows * C;
       prof_begin(K_INDUCER_CHAIN, 0, Mi * Cd * 6, s);
@@ -506,14 +521,14 @@ int run_eval(gecco_engine* e, const Workspace& w, const float* xin, const float*
       if (!kv_done) {
         g = gemm_base(w.h3, C, L.kv_w, C, irows, 2 * C, C, I, I);
         g.bias = lw[GECCO_LW_UNPOOL_IN_B] + C;
-        g.out_bf16 = w.khv; g.ldo16 = 2 * C;
+        g.out_bf16 = khv_l; g.ldo16 = 2 * C;
         TRYP(K_INDUCER_CHAIN, 4 * Mi * Cd * Cd, Mi * Cd * 6 + 4 * Cd * Cd, launch_gemm(g, s));
       }
       gecco_unpool_args u = {};
-      u.q = w.big + 2 * C; u.ldq = C3; u.kv = w.khv; u.ldkv = 2 * C; u.v_off = C;
+      u.q = w.big + 2 * C; u.ldq = C3; u.kv = khv_l; u.ldkv = 2 * C; u.v_off = C;
       u.clouds = clouds; u.rows_per_cloud = Np; u.heads = H; u.head_dim = hd; u.inducers = I;
       u.out_bf16 = w.y; u.ldo = C;
-      u.vt_scratch = w.vt; u.vt_ready = kv_done ? 1 : 0;
+      u.vt_scratch = vt_l; u.vt_ready = kv_done ? 1 : 0;
       TRYP(K_UNPOOL_ATTN, 4 * Mv * I * Cd, Mv * Cd * 4 + Mi * Cd * 4, launch_unpool_attention(u, s));
       // x = x + out_proj(attn)  (:164), bf16 copy, statistics for mlp_norm
       g = gemm_base(w.y, C, L.out_w, C, rows, C, C, Np, points);
@@ -929,7 +944,7 @@ extern "C" int gecco_sample(gecco_engine* e, const gecco_sample_args* a, void* s
 namespace gecco {
 namespace {
 struct UpsampleLayout {
-  size_t carve_bytes, cache_off, seed_in_off, seed_out_off, total;
+  size_t carve_bytes, cache_off, seed_in_off, seed_out_off, khv_off, vt_off, total;
 };
 UpsampleLayout upsample_layout(const gecco_engine* e, int clouds, int seed_points, int new_points) {
   UpsampleLayout u;
@@ -942,6 +957,10 @@ UpsampleLayout upsample_layout(const gecco_engine* e, int clouds, int seed_point
   off = align_up(off + (size_t)clouds * seed_points * 3 * sizeof(float));
   u.seed_out_off = off;
   off = align_up(off + (size_t)clouds * seed_points * 3 * sizeof(float));
+  u.khv_off = off;
+  off = align_up(off + (size_t)e->d.n_layers * clouds * e->d.num_inducers * 2 * e->d.feature_dim * sizeof(__nv_bfloat16));
+  u.vt_off = off;
+  off = align_up(off + (size_t)e->d.n_layers * clouds * e->d.num_inducers * e->d.feature_dim * sizeof(__nv_bfloat16));
   u.total = off;
   return u;
 }
@@ -985,6 +1004,10 @@ int enqueue_upsample_step(gecco_engine* e, const gecco_upsample_step_args* a, cu
   float* cache = reinterpret_cast<float*>(base + u.cache_off);
   float* seed_in = reinterpret_cast<float*>(base + u.seed_in_off);
   float* seed_out = reinterpret_cast<float*>(base + u.seed_out_off);
+  KvCache kv_write = {reinterpret_cast<__nv_bfloat16*>(base + u.khv_off), reinterpret_cast<__nv_bfloat16*>(base + u.vt_off), 1};
+  KvCache kv_read = kv_write;
+  kv_read.mode = 2;
+  if (getenv("GECCO_UPSAMPLE_KV") != nullptr && getenv("GECCO_UPSAMPLE_KV")[0] == '0') kv_read.mode = 0;  // A/B: re-project per evaluation
   const long long ns = (long long)a->clouds * a->seed_points * 3, n3 = (long long)a->clouds * a->new_points * 3;
   // data_ctx = data + randn * t_cur; full evaluation on the seed cloud, inducer states cached (:430-437)
   TRY(launch_seed_renoise(a->seed_data, a->seed_noise, (float)a->t_cur, ns, seed_in, s));
@@ -993,7 +1016,7 @@ int enqueue_upsample_step(gecco_engine* e, const gecco_upsample_step_args* a, cu
     gecco_head_args h = {};
     h.mode = 1;
     h.out_f32 = seed_out;  // the denoised seed cloud itself is not used (:431 `_`)
-    TRY(run_eval(e, ws, seed_in, nullptr, 0, (float)a->t_cur, nullptr, 0, a->clouds, a->seed_points, a->ctx, nullptr, cache, h, s));
+    TRY(run_eval(e, ws, seed_in, nullptr, 0, (float)a->t_cur, nullptr, 0, a->clouds, a->seed_points, a->ctx, nullptr, cache, h, s, &kv_write));
   }
   const Workspace w = carve(e, a->clouds, a->new_points, a->workspace);
   const double t_hat = a->t_cur + a->gamma * a->t_cur;
@@ -1008,12 +1031,12 @@ int enqueue_upsample_step(gecco_engine* e, const gecco_upsample_step_args* a, cu
     h.mode = 2;  // Euler (:452-454)
     h.x_hat = w.x_hat; h.x_next = w.x_next; h.d_cur = w.d_cur; h.xin_next = w.xin_b;
     h.t_hat = t_hat; h.t_next = a->t_next;
-    TRY(run_eval(e, w, w.xin_a, nullptr, 0, (float)t_hat, nullptr, 0, a->clouds, a->new_points, a->ctx, cache, nullptr, h, s));
+    TRY(run_eval(e, w, w.xin_a, nullptr, 0, (float)t_hat, nullptr, 0, a->clouds, a->new_points, a->ctx, cache, nullptr, h, s, kv_read.mode == 2 ? &kv_read : nullptr));
     if (!a->last_step) {  // 2nd order correction (:457-460); the result replaces x_hat
       h.mode = 3;
       h.xin_next = w.xin_a;
       h.noise_next = nullptr; h.churn_next = 0.0;
-      TRY(run_eval(e, w, w.xin_b, nullptr, 0, (float)a->t_next, nullptr, 0, a->clouds, a->new_points, a->ctx, cache, nullptr, h, s));
+      TRY(run_eval(e, w, w.xin_b, nullptr, 0, (float)a->t_next, nullptr, 0, a->clouds, a->new_points, a->ctx, cache, nullptr, h, s, kv_read.mode == 2 ? &kv_read : nullptr));
       src = w.x_hat;
     } else {
       src = w.x_next;

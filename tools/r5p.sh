@@ -1,0 +1,17 @@
+#!/bin/bash
+run() { local name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 2 --warmup 3 --config 2 --no-cpu-baseline > gpurun_out/r5p_$name.json 2> gpurun_out/r5p_$name.err; echo "bench $name $@ rc=$?"
+  python - <<PY
+import json
+for l in open('gpurun_out/r5p_$name.json'):
+    if l.startswith('{'):
+        j=json.loads(l); print({k:j.get(k) for k in ('value','ms_per_step')}, j.get('clocks',{}).get('sm_mhz')); print([(k['name'], k['ms']) for k in j.get('kernel_classes', []) if k['name'] in ('mlp_fused','gemm_unpool_out','gemm_kv_q','unpool_attention','pool_attention')])
+PY
+}
+run base X=1
+run un128 GECCO_HINT_UNPOOL=128
+run un129 GECCO_HINT_UNPOOL=129
+run un1 GECCO_HINT_UNPOOL=1
+run kvq128 GECCO_HINT_KVQ=128
+run kvq1 GECCO_HINT_KVQ=1
+run base2 X=1
