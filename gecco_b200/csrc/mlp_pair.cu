@@ -64,7 +64,8 @@ struct MParams {
   const float* n_t; int n_t_stride;
   const float *n_scale_w, *n_scale_b, *n_bias_w, *n_bias_b;
   long long* dbg;
-  int hints;  // GECCO_HINT_MLP: L2 residency hints, bits 0-1 A loads, 2-3 residual loads, 4-5 fp32 stores, 6-7 bf16 stores
+  int hints;  // GECCO_HINT_MLP: L2 residency hints, bits 0-1 A loads, 2-3 residual loads, 4-5 fp32 stores, 6-7 bf16 stores,
+              // 8-9 hidden-scratch stores, 10-11 hidden-scratch loads
   int rev;    // GECCO_REV & 2: row blocks are walked from the end
   int respf;  // GECCO_MLP_RESPF (development): 0 residual tile -> L2 at the start of the second product, 1 per output tile, 2 never
 };
@@ -284,6 +285,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       uint32_t it = 0;
       long long w_b1 = 0, w_a = 0, w_hr = 0, w_hs = 0, w_b2 = 0;
       const long long t_start = clock64();
+      const uint64_t h_pol = l2_policy((p.hints >> 10) & 3);  // hidden k-blocks coming back from the scratch
       for (int pb = pair; pb < p.num_pair_blocks; pb += num_pairs, ++it) {
         const int m0 = RB(pb) * 2 * BM + (int)rank * BM;
         // first product: A k-blocks once per row block, W1 half tiles per (tile, k-block)
@@ -319,7 +321,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (nb == 0 && kb % (BN / BK) == 0) TW(w_hr, &h_ready[kb / (BN / BK)], it & 1u);
             TW(w_hs, &a_empty[slot], (fill & 1u) ^ 1u);
             if (rank == 0) mbar_arrive_expect_tx(&h_full[slot], 2 * A_KB_BYTES);
-            tma_load_2d_pair(sA + slot * A_KB_BYTES, &tma_hl, &h_full[slot], kb * BK, srow);
+            tma_load_2d_pair_h(sA + slot * A_KB_BYTES, &tma_hl, &h_full[slot], kb * BK, srow, h_pol);
             TW(w_b2, &b_empty[stage], bphase ^ 1u);
             if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2 * B_STAGE_BYTES);
             tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tma_w2, &b_full[stage], kb * BK, wrow);
@@ -607,8 +609,10 @@ int launch_mlp_pair(const gecco_mlp_args& a, cudaStream_t stream) {
   if (rev < 0) { const char* v = getenv("GECCO_REV"); rev = v ? atoi(v) : 2; }
   p.rev = (rev & 2) ? 1 : 0;
   static int hints = -1;
-  if (hints < 0) { const char* v = getenv("GECCO_HINT_MLP"); hints = v ? atoi(v) : 5; }  // A and residual are read once: evict_first
+  if (hints < 0) { const char* v = getenv("GECCO_HINT_MLP"); hints = v ? atoi(v) : 2565; }  // A, residual read once: evict_first; hidden scratch: evict_last
   p.hints = hints;
+  p.u.hints = ((hints >> 8) & 3) << 6;  // hidden tiles going to the scratch (bits 8-9), coming back (bits 10-11)
+  p.d.hints = 0;
 
   static bool attr_set = false;
   if (!attr_set) {
