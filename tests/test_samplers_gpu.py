@@ -88,3 +88,33 @@ def test_log_likelihood_matches_oracle(cuda, kind):
     assert rms(got["latent"].cpu() - ref["latent"]) / rms(ref["latent"]) < 1e-2
     # measured on B200: prior 1.6e-5 / 1.6e-6, divergence integral 4e-5 / 9.4e-4, log p 6e-5 / 2.9e-3 (uncond / cond)
     assert rel("prior_logp") < 1e-3 and rel("delta_jacobian") < 5e-3 and rel("logp") < 1e-2
+
+
+def test_log_likelihood_uvl_matches_oracle(cuda):
+    """The same with the UVL reparametrisation (256^2-style pyramid): the lookup positions go through tanh / exp / the
+    camera, and the log-det of data -> diffusion is a full 3 x 3 block per point."""
+    import gecco_b200 as G
+
+    B, N, steps = 2, 256, 5
+    rp = synth.UVL_REPARAM
+    feats = synth.synth_features(B, (64, 32, 16), 21)
+    sd = synth.tame(synth.full_state_dict("cond", "uvl", rp["mean"], rp["sigma"], 1234), 0.15)
+    model = build("cond", "uvl", rp["mean"], rp["sigma"], 180.0, None, cuda, feats, state_dict=sd)
+    K = synth.camera(B, synth.K_TASKONOMY)
+    ctx = G.Context3d(image=torch.zeros(B, 3, 8, 8, device=cuda), K=K.to(cuda))
+    cfg = O.OracleConfig(kind="cond", reparam="uvl", sigma_max=180.0)
+    data = O.diffusion_to_data(cfg, sd, torch.randn(B, N, 3, generator=synth.gen(2)) * 0.8, K)
+    noise = (torch.randint(0, 2, (1, B, N, 3), generator=synth.gen(3)) * 2 - 1).float()
+    ref = O.log_likelihood(cfg, sd, data, noise, feats, K, num_steps=steps)
+    got = model.log_likelihood(data.to(cuda), ctx, noise=noise.to(cuda), num_steps=steps, return_details=True)
+    rel = lambda k: ((got[k].cpu() - ref[k]).abs() / ref[k].abs().clamp_min(1.0)).max().item()
+    print("log-likelihood uvl", {k: rel(k) for k in ("prior_logp", "delta_jacobian", "delta_reparam", "logp")},
+          "latent", rms(got["latent"].cpu() - ref["latent"]) / rms(ref["latent"]))
+    assert rel("delta_reparam") < 1e-4
+    assert rms(got["latent"].cpu() - ref["latent"]) / rms(ref["latent"]) < 1e-2
+    # log p is a sum of large terms of both signs here: its error is held against their magnitude, not against |log p|
+    scale = ref["prior_logp"].abs() + ref["delta_jacobian"].abs() + ref["delta_reparam"].abs()
+    e_logp = ((got["logp"].cpu() - ref["logp"]).abs() / scale).max().item()
+    print("log-likelihood uvl: log p error relative to the sum of its terms", e_logp)
+    # measured on B200: prior 7.7e-6, divergence integral 6.1e-3, log-det 6e-7, latent 2.9e-3
+    assert rel("prior_logp") < 1e-3 and rel("delta_jacobian") < 2e-2 and e_logp < 1e-2
