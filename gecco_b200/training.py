@@ -37,16 +37,20 @@ from . import ops
 # ----------------------------------------------------------------------------------------------------------------------
 # Linear layers on the tcgen05 GEMM
 class TCLinear(torch.autograd.Function):
-    """y = x W^T + b with x [M, K], W [N, K]: forward and dX on `gecco_gemm`, dW on cuBLAS, db a column sum."""
+    """y = x W^T + b with x [M, K], W [N, K]: forward and dX on `gecco_gemm`, dW on cuBLAS, db a column sum (one GEMV-like
+    pass).  x may already be bf16 (attention outputs) and y may be requested in bf16 (attention inputs): the tensors between
+    a projection and an attention core then never exist in fp32, and their gradients arrive / leave in bf16 as well."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor | None):
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor | None, out_bf16: bool = False):
         xb = x.detach().to(torch.bfloat16).contiguous()
         wb = weight.detach().to(torch.bfloat16).contiguous()
-        y, _ = ops.gemm(xb, wb, bias=None if bias is None else bias.detach().float().contiguous(), out_f32=True)
+        y32, y16 = ops.gemm(xb, wb, bias=None if bias is None else bias.detach().float().contiguous(), out_f32=not out_bf16,
+                            out_bf16=out_bf16)
         ctx.save_for_backward(xb, wb)
         ctx.has_bias = bias is not None
-        return y
+        ctx.x_bf16 = x.dtype == torch.bfloat16
+        return y16 if out_bf16 else y32
 
     @staticmethod
     def backward(ctx, dy: Tensor):
@@ -55,12 +59,28 @@ class TCLinear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX [M, K] = dY [M, N] . W [N, K]: the same kernel with W^T as its (row-major [K, N]) weight operand
-            dx, _ = ops.gemm(dyb, wb.t().contiguous(), out_f32=True)
+            d32, d16 = ops.gemm(dyb, wb.t().contiguous(), out_f32=not ctx.x_bf16, out_bf16=ctx.x_bf16)
+            dx = d16 if ctx.x_bf16 else d32
         if ctx.needs_input_grad[1]:
             dw = _mm_f32(dyb.t(), xb)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=0)
-        return dx, dw, db
+            db = _colsum(dy)
+        return dx, dw, db, None
+
+
+_ONES: dict = {}
+
+
+def _colsum(dy: Tensor) -> Tensor:
+    """Column sums of dY [M, N] in fp32 as ONE pass (ones^T . dY on the library GEMM / GEMV) instead of torch's strided
+    reduction kernel."""
+    key = (dy.device, dy.dtype, dy.shape[0])
+    ones = _ONES.get(key)
+    if ones is None:
+        ones = _ONES[key] = torch.ones(dy.shape[0], device=dy.device, dtype=dy.dtype)
+    if dy.dtype == torch.float32:
+        return torch.mv(dy.t(), ones)
+    return _mm_f32(ones.unsqueeze(0), dy).squeeze(0)
 
 
 def _mm_f32(a: Tensor, b: Tensor) -> Tensor:
@@ -86,17 +106,18 @@ def input_gradients():
         _INPUT_GRAD_ONLY = prev
 
 
-def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None) -> Tensor:
-    """F.linear on [..., K]; through the tcgen05 GEMM when the shape allows (K, N multiples of 8, CUDA)."""
+def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None, out_bf16: bool = False) -> Tensor:
+    """F.linear on [..., K]; through the tcgen05 GEMM when the shape allows (K, N multiples of 8, CUDA).  `out_bf16`: the
+    result feeds an attention core and is produced in bf16 directly (CUDA only; fp32 elsewhere)."""
     K, N = lin_w.shape[1], lin_w.shape[0]
     if _INPUT_GRAD_ONLY:
         lin_w, lin_b = lin_w.detach(), None if lin_b is None else lin_b.detach()
     if x.is_cuda and K % 8 == 0 and N % 8 == 0 and x.numel() > 0 and os.environ.get("GECCO_TRAIN_TC", "1") != "0":
-        y = TCLinear.apply(x.reshape(-1, K), lin_w, lin_b)
+        y = TCLinear.apply(x.reshape(-1, K), lin_w, lin_b, out_bf16)
         return y.view(*x.shape[:-1], N)
     if x.is_cuda:  # library arm of the A/B (GECCO_TRAIN_TC=0) and odd shapes: cuBLAS with the same bf16 operands
         y = F.linear(x.to(torch.bfloat16), lin_w.to(torch.bfloat16), None if lin_b is None else lin_b.to(torch.bfloat16))
-        return y.float()
+        return y if out_bf16 else y.float()
     return F.linear(x, lin_w, lin_b)
 
 
@@ -207,8 +228,9 @@ def mlp(mod, x: Tensor) -> Tensor:
 
 
 def _sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+    """Attention core; bf16 in and OUT on CUDA (the following projection takes bf16), fp32 on the CPU test path."""
     if q.is_cuda:
-        return F.scaled_dot_product_attention(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)).float()
+        return F.scaled_dot_product_attention(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16))
     return F.scaled_dot_product_attention(q, k, v)
 
 
@@ -216,7 +238,7 @@ def attention_pool(pool, y: Tensor) -> Tensor:
     """models/set_transformer.py:47-65."""
     B, N, C = y.shape
     H, d = pool.num_heads, pool.dims_per_head
-    kv = linear(y, pool.kv_proj.weight, None)  # columns ordered (t h d)
+    kv = linear(y, pool.kv_proj.weight, None, out_bf16=True)  # columns ordered (t h d)
     k = kv[..., :C].reshape(B, N, H, d).transpose(1, 2)
     v = kv[..., C:].reshape(B, N, H, d).transpose(1, 2)
     q = pool.inducers.expand(B, -1, -1, -1)
@@ -231,8 +253,8 @@ def unpool(mha: nn.MultiheadAttention, y: Tensor, h: Tensor) -> Tensor:
     d = C // H
     w, b = mha.in_proj_weight, mha.in_proj_bias
     bq, bkv = (None, None) if b is None else (b[:C], b[C:])
-    q = linear(y, w[:C], bq).reshape(B, N, H, d).transpose(1, 2)
-    kv = linear(h, w[C:], bkv)
+    q = linear(y, w[:C], bq, out_bf16=True).reshape(B, N, H, d).transpose(1, 2)
+    kv = linear(h, w[C:], bkv, out_bf16=True)
     k = kv[..., :C].reshape(B, I, H, d).transpose(1, 2)
     v = kv[..., C:].reshape(B, I, H, d).transpose(1, 2)
     a = _sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
