@@ -42,13 +42,15 @@ class TCLinear(torch.autograd.Function):
     a projection and an attention core then never exist in fp32, and their gradients arrive / leave in bf16 as well."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor | None, out_bf16: bool = False):
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor | None, out_bf16: bool = False, residual: Tensor | None = None):
         xb = x.detach().to(torch.bfloat16).contiguous()
         wb = weight.detach().to(torch.bfloat16).contiguous()
+        # `residual` [M, N] fp32 is added in the GEMM epilogue (the layer's `x + f(x)`): no separate element-wise pass
         y32, y16 = ops.gemm(xb, wb, bias=None if bias is None else bias.detach().float().contiguous(), out_f32=not out_bf16,
-                            out_bf16=out_bf16)
+                            out_bf16=out_bf16, res=None if residual is None else residual.detach().contiguous())
         ctx.save_for_backward(xb, wb)
         ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
         ctx.x_bf16 = x.dtype == torch.bfloat16
         return y16 if out_bf16 else y32
 
@@ -65,7 +67,7 @@ class TCLinear(torch.autograd.Function):
             dw = _mm_f32(dyb.t(), xb)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _colsum(dy)
-        return dx, dw, db, None
+        return dx, dw, db, None, (dy if ctx.has_res and ctx.needs_input_grad[4] else None)
 
 
 _ONES: dict = {}
@@ -106,19 +108,23 @@ def input_gradients():
         _INPUT_GRAD_ONLY = prev
 
 
-def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None, out_bf16: bool = False) -> Tensor:
+def linear(x: Tensor, lin_w: Tensor, lin_b: Tensor | None, out_bf16: bool = False, residual: Tensor | None = None) -> Tensor:
     """F.linear on [..., K]; through the tcgen05 GEMM when the shape allows (K, N multiples of 8, CUDA).  `out_bf16`: the
     result feeds an attention core and is produced in bf16 directly (CUDA only; fp32 elsewhere)."""
     K, N = lin_w.shape[1], lin_w.shape[0]
     if _INPUT_GRAD_ONLY:
         lin_w, lin_b = lin_w.detach(), None if lin_b is None else lin_b.detach()
     if x.is_cuda and K % 8 == 0 and N % 8 == 0 and x.numel() > 0 and os.environ.get("GECCO_TRAIN_TC", "1") != "0":
-        y = TCLinear.apply(x.reshape(-1, K), lin_w, lin_b, out_bf16)
-        return y.view(*x.shape[:-1], N)
+        fuse = residual is not None and not out_bf16 and residual.dtype == torch.float32 and _fused()
+        y = TCLinear.apply(x.reshape(-1, K), lin_w, lin_b, out_bf16, residual.reshape(-1, N) if fuse else None)
+        y = y.view(*x.shape[:-1], N)
+        return y if fuse or residual is None else residual + y
     if x.is_cuda:  # library arm of the A/B (GECCO_TRAIN_TC=0) and odd shapes: cuBLAS with the same bf16 operands
         y = F.linear(x.to(torch.bfloat16), lin_w.to(torch.bfloat16), None if lin_b is None else lin_b.to(torch.bfloat16))
-        return y if out_bf16 else y.float()
-    return F.linear(x, lin_w, lin_b)
+        y = y if out_bf16 else y.float()
+        return y if residual is None else residual + y
+    y = F.linear(x, lin_w, lin_b)
+    return y if residual is None else residual + y
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -213,18 +219,23 @@ def gaussian_activation(act, x: Tensor) -> Tensor:
     return (y - 0.7) / 0.28 if act.normalized else y
 
 
-def mlp(mod, x: Tensor) -> Tensor:
-    """models/mlp.py:5-39 (an nn.Sequential of Linear / activation modules)."""
+def mlp(mod, x: Tensor, residual: Tensor | None = None) -> Tensor:
+    """models/mlp.py:5-39 (an nn.Sequential of Linear / activation modules); `residual` is added to the result (in the
+    epilogue of the last projection)."""
     from .models.activation import GaussianActivation
 
-    for m in mod:
+    mods = list(mod)
+    for i, m in enumerate(mods):
         if isinstance(m, nn.Linear):
-            x = linear(x, m.weight, m.bias)
+            last = i == len(mods) - 1
+            x = linear(x, m.weight, m.bias, residual=residual if last else None)
+            if last:
+                residual = None
         elif isinstance(m, GaussianActivation):
             x = gaussian_activation(m, x)
         else:
             x = m(x)
-    return x
+    return x if residual is None else residual + x
 
 
 def _sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
@@ -246,7 +257,7 @@ def attention_pool(pool, y: Tensor) -> Tensor:
     return linear(attn, pool.out_proj.weight, None)
 
 
-def unpool(mha: nn.MultiheadAttention, y: Tensor, h: Tensor) -> Tensor:
+def unpool(mha: nn.MultiheadAttention, y: Tensor, h: Tensor, residual: Tensor | None = None) -> Tensor:
     """nn.MultiheadAttention(batch_first)(query = y, key = value = h), models/set_transformer.py:90,112."""
     B, N, C = y.shape
     I, H = h.shape[1], mha.num_heads
@@ -258,7 +269,7 @@ def unpool(mha: nn.MultiheadAttention, y: Tensor, h: Tensor) -> Tensor:
     k = kv[..., :C].reshape(B, I, H, d).transpose(1, 2)
     v = kv[..., C:].reshape(B, I, H, d).transpose(1, 2)
     a = _sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
-    return linear(a, mha.out_proj.weight, mha.out_proj.bias)
+    return linear(a, mha.out_proj.weight, mha.out_proj.bias, residual=residual)
 
 
 def broadcasting_layer(layer, x: Tensor, t: Tensor) -> Tensor:
@@ -269,9 +280,9 @@ def broadcasting_layer(layer, x: Tensor, t: Tensor) -> Tensor:
     h = adagn(bc.norm_1, h, t)
     h = mlp(bc.mlp, h)
     h = adagn(bc.norm_2, h, t)
-    x = x + unpool(bc.unpool, y, h)
+    x = unpool(bc.unpool, y, h, residual=x)  # x + unpool(...): the addition runs in the out-projection's epilogue
     y = adagn(layer.mlp_norm, x, t)
-    return x + mlp(layer.mlp, y)
+    return mlp(layer.mlp, y, residual=x)
 
 
 def set_transformer(st, x: Tensor, t: Tensor) -> Tensor:
