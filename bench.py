@@ -439,6 +439,9 @@ def run_train(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_text(cfg, B), "baseline_config": 5, "clouds_per_gpu": B, "points": POINTS,
                        "l2": "no flush needed: one step streams tens of GB of activations per GPU",
+                       "precision": "bf16 operands / fp32 accumulate, residual stream, statistics and master weights; the ConvNeXt "
+                                    "conditioner under bf16 autocast (the reference trains with precision='16-mixed'), "
+                                    "GECCO_TRAIN_COND_AUTOCAST=0 for fp32",
                        "parallelism": f"dp{world} (batch sharded on dim 0; gradient all-reduce in "
                                       f"{len(trainer.reducer.buckets)} buckets overlapped with backward)"},
             "e2e": {"value": clouds / (ms_e2e * 1e-3), "unit": "clouds/s",

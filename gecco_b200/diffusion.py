@@ -9,6 +9,7 @@ the head kernel of each evaluation (float64 state, schedule computed on the host
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Sequence
 
 import torch
@@ -158,7 +159,15 @@ class Diffusion(_Base):
     def forward(self, data: Tensor, sigma: Tensor, raw_context: Any | None, post_context: Any | None = None,
                 do_cache: bool = False, cache: Any | None = None):
         if post_context is None:
-            post_context = self.conditioner(raw_context)
+            # the conditioner of a TRAINING step runs under bf16 autocast, like the rest of the network and like the
+            # reference's own `precision="16-mixed"` runs (example_configs/*.py:74,102); GECCO_TRAIN_COND_AUTOCAST=0: fp32.
+            # Sampling / validation keep the fp32 conditioner (parity of the feature pyramid to 1e-7).
+            if (self.training and torch.is_grad_enabled() and raw_context is not None and raw_context.image.is_cuda
+                    and os.environ.get("GECCO_TRAIN_COND_AUTOCAST", "1") != "0"):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    post_context = self.conditioner(raw_context)
+            else:
+                post_context = self.conditioner(raw_context)
         return self.backbone(data, sigma, raw_context, post_context, do_cache, cache)
 
     @property
