@@ -408,6 +408,8 @@ def run_train(args):
     E.launch_count(reset=True)
     ms, loss = timed(step_resident, args.steps)
     launches = E.launch_count(reset=True)
+    if trainer.graph_mode:  # the captured forward + backward replays its library kernels without passing the C ABI again
+        launches += trainer.graph_library_launches * args.steps
     ms_e2e, _ = timed(step_e2e, args.steps)
     clk = clocks.stop() if clocks else None
     mem_gb = torch.cuda.max_memory_allocated(device) / 2**30

@@ -530,6 +530,7 @@ class Trainer:
         self.steps = 0
         self._graph = None
         self._static = None
+        self.graph_library_launches = 0
 
     def step(self, batch) -> Tensor:
         """One optimisation step on `batch` = (data [B, N, 3], Context3d | None); returns the (detached) loss."""
@@ -577,10 +578,15 @@ class Trainer:
                 self.model.training_step(static_batch, 0).backward()
         torch.cuda.current_stream(data.device).wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
+        from . import engine as _engine
+
+        before = _engine.launch_count()
         with torch.cuda.graph(self._graph):
             self.state.g.zero_()
             loss = self.model.training_step(static_batch, 0)
             loss.backward()
+        # launches of this library's kernels recorded in the graph (each replay issues them again without passing the C ABI)
+        self.graph_library_launches = _engine.launch_count() - before
         self._static = dict(key=key, tensors=self._tensors(static_batch), loss=loss.detach())
 
     @contextlib.contextmanager
