@@ -40,7 +40,7 @@ def test_log_likelihood_host_logic_matches_oracle(kind, reparam):
     import gecco_b200 as G
 
     torch.manual_seed(0)
-    B, N, L, steps = 2, 48, 2, 5
+    B, N, L, steps = 2, 32, 2, 3
     if reparam == "uvl":
         rp, Kc, smax = synth.UVL_REPARAM, synth.K_TASKONOMY, 180.0
     else:
@@ -52,13 +52,13 @@ def test_log_likelihood_host_logic_matches_oracle(kind, reparam):
     K = synth.camera(B, Kc) if kind == "cond" else None
     ctx = G.Context3d(image=torch.zeros(B, 3, 8, 8), K=K) if kind == "cond" else None
     data = O.diffusion_to_data(cfg, sd, torch.randn(B, N, 3, generator=synth.gen(2)) * 0.8, K)
-    noise = (torch.randint(0, 2, (2, B, N, 3), generator=synth.gen(3)) * 2 - 1).float()
+    noise = (torch.randint(0, 2, (1, B, N, 3), generator=synth.gen(3)) * 2 - 1).float()
     ref = O.log_likelihood(cfg, sd, data, noise, feats, K, num_steps=steps)
     got = model.log_likelihood(data, ctx, noise=noise, num_steps=steps, return_details=True)
     for k in ("prior_logp", "delta_reparam", "delta_jacobian", "logp"):
         assert torch.allclose(got[k], ref[k], rtol=2e-4, atol=2e-3), (k, got[k], ref[k])
     assert torch.allclose(got["latent"], ref["latent"], rtol=1e-4, atol=1e-4)
     # drawn probes: deterministic for a seeded generator, [B] float64
-    a = model.log_likelihood(data, ctx, rng=synth.gen(9), num_steps=3)
-    b = model.log_likelihood(data, ctx, rng=synth.gen(9), num_steps=3)
+    a = model.log_likelihood(data, ctx, rng=synth.gen(9), num_steps=2)
+    b = model.log_likelihood(data, ctx, rng=synth.gen(9), num_steps=2)
     assert a.shape == (B,) and a.dtype == torch.float64 and torch.equal(a, b)
